@@ -1,0 +1,572 @@
+// C ABI of libhs_b200.so (include/hs.h): context, device buffers, TMA descriptors, launches.
+// Replaces class hornSchunck (/root/reference/HornSchunckOF/hornSchunck.cpp:8-76) behind
+// hs_create / hs_solve / hs_destroy.  No CPU fallback anywhere in this file.
+#include "../../include/hs.h"
+
+#include <cudaTypedefs.h>
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <string>
+
+#include "hs_kernels.cuh"
+
+namespace {
+
+constexpr int TILE_R = 4;       // rows per thread in the fused kernel
+constexpr int TILE_NWARP = 12;  // warps per CTA (staged tile 128 x 48)
+
+thread_local std::string g_create_err;
+
+inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
+
+struct DevGuard {
+    int prev = -1;
+    bool ok = true;
+    explicit DevGuard(int dev) {
+        if (cudaGetDevice(&prev) != cudaSuccess) { ok = false; prev = -1; }
+        if (ok && prev != dev) ok = (cudaSetDevice(dev) == cudaSuccess);
+    }
+    ~DevGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+}  // namespace
+
+struct hs_ctx {
+    hs_config cfg{};
+    int dev = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+
+    int W = 0, H = 0, B = 1, w = 0, a = 0, RL = 0, RR = 0, T = 0;
+    double alpha = 0;
+    int pitch = 0;
+    long long plane = 0;
+    int oy0 = 0, oy1 = 0;
+    bool top_seam = false, bot_seam = false;
+
+    int frows = 0, frow0 = 0;
+    size_t fpitch = 0, fimg = 0;
+    uint8_t* d_prev = nullptr;
+    uint8_t* d_next = nullptr;
+    float* d_u[2] = {nullptr, nullptr};
+    float* d_v[2] = {nullptr, nullptr};
+    int cur = 0;
+    __half2* d_ixy = nullptr;
+    __half* d_it = nullptr;
+    float* d_inv = nullptr;
+    void* d_out = nullptr;
+    size_t out_bytes = 0;
+
+    CUtensorMap tm_u[2], tm_v[2], tm_ixy, tm_it, tm_inv;
+    int kernel_id = 0;  // 0 generic, 1 fused tile
+    int k = 1;
+
+    cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    hs_timing timing{};
+    bool uploaded = false, prepared = false;
+    std::string err;
+
+    hs::Geom geom() const {
+        hs::Geom g;
+        g.W = W; g.H = H; g.pitch = pitch; g.plane = plane; g.oy0 = oy0; g.oy1 = oy1;
+        return g;
+    }
+};
+
+namespace {
+
+int fail(hs_ctx* c, int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (c) c->err = buf; else g_create_err = buf;
+    return code;
+}
+
+#define HS_CUDA(c, call)                                                                        \
+    do {                                                                                        \
+        cudaError_t e__ = (call);                                                               \
+        if (e__ != cudaSuccess)                                                                 \
+            return fail((c), e__ == cudaErrorMemoryAllocation ? HS_ERR_OOM : HS_ERR_CUDA,       \
+                        "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__,      \
+                        __LINE__);                                                              \
+    } while (0)
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point: no -lcuda at link time.
+PFN_cuTensorMapEncodeTiled_v12000 tensor_map_encoder() {
+    static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(p);
+    }
+    return fn;
+}
+
+// rank-3 map over (x, y, pair) of a pitched plane; box = SX x SY x 1; OOB reads as zero
+int make_map(hs_ctx* c, CUtensorMap* m, void* base, CUtensorMapDataType dt, int esize, int box_x,
+             int box_y) {
+    auto enc = tensor_map_encoder();
+    if (!enc) return fail(c, HS_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+    cuuint64_t dims[3] = {(cuuint64_t)c->W, (cuuint64_t)c->H, (cuuint64_t)c->B};
+    cuuint64_t strides[2] = {(cuuint64_t)c->pitch * esize, (cuuint64_t)c->plane * esize};
+    cuuint32_t box[3] = {(cuuint32_t)box_x, (cuuint32_t)box_y, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = enc(m, dt, 3, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(c, HS_ERR_CUDA, "cuTensorMapEncodeTiled failed (CUresult %d)", (int)r);
+    return HS_OK;
+}
+
+template <int RL, int RR>
+struct Tile {
+    using TS = hs::TileShape<RL, RR, TILE_R, TILE_NWARP>;
+    static auto kernel() { return hs::k_jacobi_tile<RL, RR, TILE_R, TILE_NWARP>; }
+    static cudaError_t configure() {
+        return cudaFuncSetAttribute(kernel(), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TS::SMEM);
+    }
+    static int max_k() { return (TS::SY - 1) / std::max(1, RL + RR); }
+    static cudaError_t launch(hs_ctx* c, int kk) {
+        const int hxl = round_up(RL * kk, 4), hxr = round_up(RR * kk, 4);
+        const int hyt = RL * kk, hyb = RR * kk;
+        const int vx = TS::SX - hxl - hxr, vy = TS::SY - hyt - hyb;
+        dim3 grid((c->W + vx - 1) / vx, (c->oy1 - c->oy0 + vy - 1) / vy, c->B);
+        const float kf = 1.0f / (float)(c->w * c->w);
+        kernel()<<<grid, TS::THREADS, TS::SMEM, c->stream>>>(
+            c->tm_u[c->cur], c->tm_v[c->cur], c->tm_ixy, c->tm_it, c->tm_inv, c->d_u[c->cur ^ 1],
+            c->d_v[c->cur ^ 1], c->geom(), kk, hxl, hyt, vx, vy, kf);
+        return cudaGetLastError();
+    }
+};
+
+// dispatch on (RL, RR) = (anchor, w - 1 - anchor); returns false when no fused kernel exists
+template <typename F>
+bool tile_dispatch(int RL, int RR, F&& f) {
+    if (RL == 0 && RR == 1) { f(Tile<0, 1>{}); return true; }   // w = 2
+    if (RL == 1 && RR == 1) { f(Tile<1, 1>{}); return true; }   // w = 3
+    if (RL == 1 && RR == 2) { f(Tile<1, 2>{}); return true; }   // w = 4
+    if (RL == 2 && RR == 2) { f(Tile<2, 2>{}); return true; }   // w = 5
+    return false;
+}
+
+int env_int(const char* name, int dflt) {
+    const char* s = getenv(name);
+    return (s && *s) ? atoi(s) : dflt;
+}
+
+int ensure_out(hs_ctx* c, size_t bytes) {
+    if (c->out_bytes >= bytes) return HS_OK;
+    if (c->d_out) cudaFree(c->d_out);
+    c->d_out = nullptr;
+    c->out_bytes = 0;
+    HS_CUDA(c, cudaMalloc(&c->d_out, bytes));
+    c->out_bytes = bytes;
+    return HS_OK;
+}
+
+float ev_ms(cudaEvent_t a, cudaEvent_t b) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, a, b) != cudaSuccess) ms = 0.f;
+    return ms;
+}
+
+int do_upload(hs_ctx* c, const uint8_t* prev, size_t ps, size_t pis, const uint8_t* next, size_t ns,
+              size_t nis) {
+    if (!prev || !next) return fail(c, HS_ERR_INVALID_ARG, "null frame pointer");
+    if (ps < (size_t)c->W || ns < (size_t)c->W)
+        return fail(c, HS_ERR_INVALID_ARG, "row stride smaller than width");
+    if (c->B > 1 && (pis < ps * c->frows || nis < ns * c->frows))
+        return fail(c, HS_ERR_INVALID_ARG, "image stride smaller than one image");
+    for (int b = 0; b < c->B; ++b) {
+        HS_CUDA(c, cudaMemcpy2DAsync(c->d_prev + (size_t)b * c->fimg, c->fpitch, prev + (size_t)b * pis, ps,
+                                     c->W, c->frows, cudaMemcpyHostToDevice, c->stream));
+        HS_CUDA(c, cudaMemcpy2DAsync(c->d_next + (size_t)b * c->fimg, c->fpitch, next + (size_t)b * nis, ns,
+                                     c->W, c->frows, cudaMemcpyHostToDevice, c->stream));
+    }
+    c->uploaded = true;
+    c->prepared = false;
+    return HS_OK;
+}
+
+int do_prepare(hs_ctx* c) {
+    if (!c->uploaded) return fail(c, HS_ERR_STATE, "hs_prepare before frames were uploaded");
+    const size_t fbytes = (size_t)c->plane * c->B * sizeof(float);
+    for (int i = 0; i < 2; ++i) {
+        HS_CUDA(c, cudaMemsetAsync(c->d_u[i], 0, fbytes, c->stream));   // hornSchunck.cpp:49-50
+        HS_CUDA(c, cudaMemsetAsync(c->d_v[i], 0, fbytes, c->stream));
+    }
+    c->cur = 0;
+    dim3 block(32, 8);
+    dim3 grid((c->pitch / 4 + 31) / 32, (c->H + 7) / 8, c->B);
+    const float a2 = (float)(c->alpha * c->alpha);
+    hs::k_grad_coeff<<<grid, block, 0, c->stream>>>(c->d_prev, c->d_next, c->fpitch, c->fimg, c->frows,
+                                                    c->frow0, c->d_ixy, c->d_it, c->d_inv, c->geom(), a2);
+    HS_CUDA(c, cudaGetLastError());
+    c->timing.launches += 1;
+    c->prepared = true;
+    return HS_OK;
+}
+
+int do_iterate(hs_ctx* c, int iters) {
+    if (!c->prepared) return fail(c, HS_ERR_STATE, "hs_iterate before hs_prepare");
+    if (iters < 0) return fail(c, HS_ERR_INVALID_ARG, "negative iteration count");
+    int left = iters;
+    while (left > 0) {
+        int kk = 1;
+        cudaError_t e = cudaSuccess;
+        if (c->kernel_id == 1) {
+            kk = std::min(c->k, left);
+            tile_dispatch(c->RL, c->RR, [&](auto t) { e = decltype(t)::launch(c, kk); });
+        } else {
+            dim3 block(32, 8);
+            dim3 grid((c->W + 31) / 32, (c->oy1 - c->oy0 + 7) / 8, c->B);
+            const float kf = 1.0f / (float)(c->w * c->w);
+            hs::k_jacobi_generic<<<grid, block, 0, c->stream>>>(c->d_u[c->cur], c->d_v[c->cur], c->d_u[c->cur ^ 1],
+                                                                c->d_v[c->cur ^ 1], c->d_ixy, c->d_it, c->d_inv,
+                                                                c->geom(), c->w, c->a, kf);
+            e = cudaGetLastError();
+        }
+        if (e != cudaSuccess) return fail(c, HS_ERR_CUDA, "sweep launch failed: %s", cudaGetErrorString(e));
+        c->cur ^= 1;
+        left -= kk;
+        c->timing.launches += 1;
+    }
+    return HS_OK;
+}
+
+int do_download(hs_ctx* c, void* u, size_t us, size_t uis, void* v, size_t vs, size_t vis, int dt) {
+    if (!u || !v) return fail(c, HS_ERR_INVALID_ARG, "null output pointer");
+    if (dt != HS_F32 && dt != HS_F64) return fail(c, HS_ERR_INVALID_ARG, "bad out_dtype");
+    const size_t es = dt == HS_F64 ? 8 : 4;
+    const int rows = c->oy1 - c->oy0;
+    if (us < c->W * es || vs < c->W * es) return fail(c, HS_ERR_INVALID_ARG, "output row stride smaller than a row");
+    if (c->B > 1 && (uis < us * rows || vis < vs * rows))
+        return fail(c, HS_ERR_INVALID_ARG, "output image stride smaller than one image");
+    const char* su;
+    const char* sv;
+    if (dt == HS_F64) {
+        const long long n = c->plane * c->B;
+        int rc = ensure_out(c, (size_t)n * 2 * sizeof(double));
+        if (rc) return rc;
+        double* o = static_cast<double*>(c->d_out);
+        hs::k_widen<<<148 * 8, 256, 0, c->stream>>>(c->d_u[c->cur], c->d_v[c->cur], o, o + n, n);
+        HS_CUDA(c, cudaGetLastError());
+        c->timing.launches += 1;
+        su = reinterpret_cast<const char*>(o);
+        sv = reinterpret_cast<const char*>(o + n);
+    } else {
+        su = reinterpret_cast<const char*>(c->d_u[c->cur]);
+        sv = reinterpret_cast<const char*>(c->d_v[c->cur]);
+    }
+    for (int b = 0; b < c->B; ++b) {
+        const size_t off = ((size_t)b * c->plane + (size_t)c->oy0 * c->pitch) * es;
+        HS_CUDA(c, cudaMemcpy2DAsync(static_cast<char*>(u) + (size_t)b * uis, us, su + off, (size_t)c->pitch * es,
+                                     c->W * es, rows, cudaMemcpyDeviceToHost, c->stream));
+        HS_CUDA(c, cudaMemcpy2DAsync(static_cast<char*>(v) + (size_t)b * vis, vs, sv + off, (size_t)c->pitch * es,
+                                     c->W * es, rows, cudaMemcpyDeviceToHost, c->stream));
+    }
+    return HS_OK;
+}
+
+void destroy_impl(hs_ctx* c) {
+    if (!c) return;
+    {
+        DevGuard g(c->dev);
+        if (c->stream) cudaStreamSynchronize(c->stream);
+        cudaFree(c->d_prev); cudaFree(c->d_next);
+        for (int i = 0; i < 2; ++i) { cudaFree(c->d_u[i]); cudaFree(c->d_v[i]); }
+        cudaFree(c->d_ixy); cudaFree(c->d_it); cudaFree(c->d_inv); cudaFree(c->d_out);
+        for (auto& e : c->ev) if (e) cudaEventDestroy(e);
+        if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
+    }
+    delete c;
+}
+
+}  // namespace
+
+extern "C" {
+
+int hs_version(void) { return HS_VERSION; }
+
+const char* hs_last_error(const hs_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_err.c_str(); }
+
+int hs_create(const hs_config* cfg_in, hs_ctx** out) {
+    if (out) *out = nullptr;
+    if (!cfg_in || !out) return fail(nullptr, HS_ERR_INVALID_ARG, "null argument");
+    if (cfg_in->struct_size == 0 || cfg_in->struct_size > sizeof(hs_config))
+        return fail(nullptr, HS_ERR_INVALID_ARG, "hs_config.struct_size %u not understood (library knows %zu)",
+                    cfg_in->struct_size, sizeof(hs_config));
+    hs_config cfg{};
+    memcpy(&cfg, cfg_in, cfg_in->struct_size);
+    if (cfg.width < 1 || cfg.height < 1) return fail(nullptr, HS_ERR_INVALID_ARG, "width and height must be >= 1");
+    if (cfg.window_size < 1) return fail(nullptr, HS_ERR_INVALID_ARG, "window_size must be >= 1");
+    if (cfg.max_iterations < 0) return fail(nullptr, HS_ERR_INVALID_ARG, "max_iterations must be >= 0");
+    if (cfg.batch < 0) return fail(nullptr, HS_ERR_INVALID_ARG, "batch must be >= 1");
+    if (cfg.temporal_k < 0) return fail(nullptr, HS_ERR_INVALID_ARG, "temporal_k must be >= 0");
+    if (!(cfg.alpha == cfg.alpha)) return fail(nullptr, HS_ERR_INVALID_ARG, "alpha is NaN");
+
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(nullptr, HS_ERR_CUDA, "no usable CUDA device (%s); this library has no CPU fallback",
+                    e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+    int dev = cfg.device;
+    if (dev < 0) {
+        if (cudaGetDevice(&dev) != cudaSuccess) dev = 0;
+    }
+    if (dev >= ndev) return fail(nullptr, HS_ERR_INVALID_ARG, "device %d out of range (%d devices)", dev, ndev);
+
+    hs_ctx* c = new (std::nothrow) hs_ctx();
+    if (!c) return fail(nullptr, HS_ERR_OOM, "out of host memory");
+    c->cfg = cfg;
+    c->dev = dev;
+    c->W = cfg.width; c->H = cfg.height; c->B = cfg.batch > 0 ? cfg.batch : 1;
+    c->w = cfg.window_size; c->T = cfg.max_iterations; c->alpha = cfg.alpha;
+    c->a = c->w - c->w / 2 - 1;               // hornSchunck.cpp:54
+    c->RL = c->a; c->RR = c->w - 1 - c->a;
+    c->oy0 = cfg.out_row_begin; c->oy1 = cfg.out_row_end;
+    if (c->oy0 == 0 && c->oy1 == 0) c->oy1 = c->H;
+    c->top_seam = cfg.flags & HS_FLAG_TOP_IS_SEAM;
+    c->bot_seam = cfg.flags & HS_FLAG_BOTTOM_IS_SEAM;
+    c->pitch = round_up(c->W, 32);
+    c->plane = (long long)c->pitch * c->H;
+    c->frow0 = c->top_seam ? 1 : 0;
+    c->frows = c->H + (c->top_seam ? 1 : 0) + (c->bot_seam ? 1 : 0);
+    c->fpitch = (size_t)round_up(c->W, 128);
+    c->fimg = c->fpitch * c->frows;
+
+    auto bail = [&](int code) { g_create_err = c->err; destroy_impl(c); return code; };
+    if (c->oy0 < 0 || c->oy1 > c->H || c->oy0 >= c->oy1)
+        return bail(fail(c, HS_ERR_INVALID_ARG, "out rows [%d,%d) not inside [0,%d)", c->oy0, c->oy1, c->H));
+
+    DevGuard guard(dev);
+    if (!guard.ok) return bail(fail(c, HS_ERR_CUDA, "cudaSetDevice(%d) failed", dev));
+    cudaDeviceProp prop;
+    if ((e = cudaGetDeviceProperties(&prop, dev)) != cudaSuccess)
+        return bail(fail(c, HS_ERR_CUDA, "cudaGetDeviceProperties: %s", cudaGetErrorString(e)));
+    if (prop.major < 10)
+        return bail(fail(c, HS_ERR_UNSUPPORTED, "device %d is sm_%d%d; this library is built for sm_100a (B200) only",
+                         dev, prop.major, prop.minor));
+
+#define HS_CREATE_CUDA(call)                                                                         \
+    do {                                                                                             \
+        cudaError_t e__ = (call);                                                                    \
+        if (e__ != cudaSuccess)                                                                      \
+            return bail(fail(c, e__ == cudaErrorMemoryAllocation ? HS_ERR_OOM : HS_ERR_CUDA,         \
+                             "%s failed: %s", #call, cudaGetErrorString(e__)));                      \
+    } while (0)
+
+    if (cfg.stream) {
+        c->stream = static_cast<cudaStream_t>(cfg.stream);
+    } else {
+        HS_CREATE_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+        c->own_stream = true;
+    }
+    for (auto& ev : c->ev) HS_CREATE_CUDA(cudaEventCreate(&ev));
+
+    const size_t npx = (size_t)c->plane * c->B;
+    HS_CREATE_CUDA(cudaMalloc(&c->d_prev, c->fimg * c->B));
+    HS_CREATE_CUDA(cudaMalloc(&c->d_next, c->fimg * c->B));
+    for (int i = 0; i < 2; ++i) {
+        HS_CREATE_CUDA(cudaMalloc(&c->d_u[i], npx * sizeof(float)));
+        HS_CREATE_CUDA(cudaMalloc(&c->d_v[i], npx * sizeof(float)));
+    }
+    HS_CREATE_CUDA(cudaMalloc(&c->d_ixy, npx * sizeof(__half2)));
+    HS_CREATE_CUDA(cudaMalloc(&c->d_it, npx * sizeof(__half)));
+    HS_CREATE_CUDA(cudaMalloc(&c->d_inv, npx * sizeof(float)));
+
+    // kernel selection: fused tile kernel for w in {2,3,4,5}, generic sweep otherwise
+    const bool force_generic = (cfg.flags & HS_FLAG_FORCE_GENERIC) || env_int("HS_FORCE_GENERIC", 0);
+    bool have_tile = false;
+    int kmax = 1;
+    if (!force_generic)
+        have_tile = tile_dispatch(c->RL, c->RR, [&](auto t) {
+            using TT = decltype(t);
+            kmax = TT::max_k();
+            e = TT::configure();
+        });
+    if (have_tile && e != cudaSuccess)
+        return bail(fail(c, HS_ERR_CUDA, "cudaFuncSetAttribute(max dynamic smem): %s", cudaGetErrorString(e)));
+    if (have_tile) {
+        using TS0 = hs::TileShape<1, 1, TILE_R, TILE_NWARP>;
+        int k = cfg.temporal_k > 0 ? cfg.temporal_k : env_int("HS_K", 0);
+        if (k <= 0) k = std::max(1, 4 / std::max(1, std::max(c->RL, c->RR)));   // w=3: 4, w=5: 2
+        k = std::min(k, kmax);
+        // keep a useful centre: at least a quarter of the staged rows must be output rows
+        while (k > 1 && TS0::SY - (c->RL + c->RR) * k < TS0::SY / 4) --k;
+        c->k = k;
+        c->kernel_id = 1;
+        int rc;
+        for (int i = 0; i < 2; ++i) {
+            if ((rc = make_map(c, &c->tm_u[i], c->d_u[i], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, TS0::SX, TS0::SY))) return bail(rc);
+            if ((rc = make_map(c, &c->tm_v[i], c->d_v[i], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, TS0::SX, TS0::SY))) return bail(rc);
+        }
+        if ((rc = make_map(c, &c->tm_ixy, c->d_ixy, CU_TENSOR_MAP_DATA_TYPE_UINT32, 4, TS0::SX, TS0::SY))) return bail(rc);
+        if ((rc = make_map(c, &c->tm_it, c->d_it, CU_TENSOR_MAP_DATA_TYPE_UINT16, 2, TS0::SX, TS0::SY))) return bail(rc);
+        if ((rc = make_map(c, &c->tm_inv, c->d_inv, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, TS0::SX, TS0::SY))) return bail(rc);
+    } else {
+        c->k = 1;
+        c->kernel_id = 0;
+    }
+    // a seam needs k sweeps' worth of halo rows between the buffer edge and the output rows
+    if ((c->top_seam && c->oy0 < c->RL * c->k) || (c->bot_seam && c->H - c->oy1 < c->RR * c->k))
+        return bail(fail(c, HS_ERR_INVALID_ARG,
+                         "row slab needs %d halo rows above and %d below its output rows for k=%d (have %d / %d)",
+                         c->RL * c->k, c->RR * c->k, c->k, c->oy0, c->H - c->oy1));
+    c->timing.temporal_k = c->k;
+    c->timing.kernel_id = c->kernel_id;
+    *out = c;
+    return HS_OK;
+#undef HS_CREATE_CUDA
+}
+
+void hs_destroy(hs_ctx* ctx) { destroy_impl(ctx); }
+
+int hs_upload(hs_ctx* c, const uint8_t* prev, size_t ps, size_t pis, const uint8_t* next, size_t ns, size_t nis) {
+    if (!c) return HS_ERR_INVALID_ARG;
+    DevGuard g(c->dev);
+    return do_upload(c, prev, ps, pis, next, ns, nis);
+}
+
+int hs_prepare(hs_ctx* c) {
+    if (!c) return HS_ERR_INVALID_ARG;
+    DevGuard g(c->dev);
+    return do_prepare(c);
+}
+
+int hs_iterate(hs_ctx* c, int iterations) {
+    if (!c) return HS_ERR_INVALID_ARG;
+    DevGuard g(c->dev);
+    return do_iterate(c, iterations);
+}
+
+int hs_solve_device(hs_ctx* c) {
+    if (!c) return HS_ERR_INVALID_ARG;
+    DevGuard g(c->dev);
+    c->timing.launches = 0;
+    int rc = do_prepare(c);
+    if (rc) return rc;
+    return do_iterate(c, c->T);
+}
+
+int hs_download(hs_ctx* c, void* u, size_t us, size_t uis, void* v, size_t vs, size_t vis, int dt) {
+    if (!c) return HS_ERR_INVALID_ARG;
+    DevGuard g(c->dev);
+    int rc = do_download(c, u, us, uis, v, vs, vis, dt);
+    if (rc) return rc;
+    HS_CUDA(c, cudaStreamSynchronize(c->stream));
+    return HS_OK;
+}
+
+int hs_sync(hs_ctx* c) {
+    if (!c) return HS_ERR_INVALID_ARG;
+    DevGuard g(c->dev);
+    HS_CUDA(c, cudaStreamSynchronize(c->stream));
+    return HS_OK;
+}
+
+int hs_solve(hs_ctx* c, const uint8_t* prev, size_t ps, size_t pis, const uint8_t* next, size_t ns, size_t nis,
+             void* u, size_t us, size_t uis, void* v, size_t vs, size_t vis, int dt) {
+    if (!c) return HS_ERR_INVALID_ARG;
+    DevGuard g(c->dev);
+    c->timing.launches = 0;
+    int rc;
+    HS_CUDA(c, cudaEventRecord(c->ev[0], c->stream));
+    if ((rc = do_upload(c, prev, ps, pis, next, ns, nis))) return rc;
+    HS_CUDA(c, cudaEventRecord(c->ev[1], c->stream));
+    if ((rc = do_prepare(c))) return rc;
+    HS_CUDA(c, cudaEventRecord(c->ev[2], c->stream));
+    if ((rc = do_iterate(c, c->T))) return rc;
+    HS_CUDA(c, cudaEventRecord(c->ev[3], c->stream));
+    if ((rc = do_download(c, u, us, uis, v, vs, vis, dt))) return rc;
+    HS_CUDA(c, cudaEventRecord(c->ev[4], c->stream));
+    HS_CUDA(c, cudaStreamSynchronize(c->stream));
+    c->timing.h2d_ms = ev_ms(c->ev[0], c->ev[1]);
+    c->timing.prepare_ms = ev_ms(c->ev[1], c->ev[2]);
+    c->timing.iterate_ms = ev_ms(c->ev[2], c->ev[3]);
+    c->timing.d2h_ms = ev_ms(c->ev[3], c->ev[4]);
+    c->timing.total_ms = ev_ms(c->ev[0], c->ev[4]);
+    return HS_OK;
+}
+
+int hs_gradients(hs_ctx* c, const uint8_t* prev, size_t ps, const uint8_t* next, size_t ns, void* gx, void* gy,
+                 void* gt, size_t os, int dt) {
+    if (!c) return HS_ERR_INVALID_ARG;
+    if (c->B != 1) return fail(c, HS_ERR_UNSUPPORTED, "hs_gradients needs a batch == 1 context");
+    if (!gx || !gy || !gt) return fail(c, HS_ERR_INVALID_ARG, "null output pointer");
+    if (dt != HS_F32 && dt != HS_F64) return fail(c, HS_ERR_INVALID_ARG, "bad out_dtype");
+    const size_t es = dt == HS_F64 ? 8 : 4;
+    if (os < c->W * es) return fail(c, HS_ERR_INVALID_ARG, "output row stride smaller than a row");
+    DevGuard g(c->dev);
+    c->timing.launches = 0;
+    int rc;
+    if ((rc = do_upload(c, prev, ps, 0, next, ns, 0))) return rc;
+    if ((rc = do_prepare(c))) return rc;
+    const long long n = c->plane;
+    if ((rc = ensure_out(c, (size_t)n * 3 * es))) return rc;
+    char* o = static_cast<char*>(c->d_out);
+    if (dt == HS_F64) {
+        double* d = reinterpret_cast<double*>(o);
+        hs::k_unpack_grad<double><<<148 * 8, 256, 0, c->stream>>>(c->d_ixy, c->d_it, d, d + n, d + 2 * n, n);
+    } else {
+        float* d = reinterpret_cast<float*>(o);
+        hs::k_unpack_grad<float><<<148 * 8, 256, 0, c->stream>>>(c->d_ixy, c->d_it, d, d + n, d + 2 * n, n);
+    }
+    HS_CUDA(c, cudaGetLastError());
+    c->timing.launches += 1;
+    void* outs[3] = {gx, gy, gt};
+    for (int i = 0; i < 3; ++i)
+        HS_CUDA(c, cudaMemcpy2DAsync(outs[i], os, o + ((size_t)i * n + (size_t)c->oy0 * c->pitch) * es,
+                                     (size_t)c->pitch * es, c->W * es, c->oy1 - c->oy0, cudaMemcpyDeviceToHost,
+                                     c->stream));
+    HS_CUDA(c, cudaStreamSynchronize(c->stream));
+    return HS_OK;
+}
+
+int hs_get_device_view(hs_ctx* c, hs_device_view* o) {
+    if (!c || !o) return HS_ERR_INVALID_ARG;
+    o->prev = c->d_prev; o->next = c->d_next;
+    o->frame_pitch = c->fpitch; o->frame_pair_stride = c->fimg;
+    o->frame_rows = c->frows; o->frame_row0 = c->frow0;
+    o->u = c->d_u[c->cur]; o->v = c->d_v[c->cur];
+    o->flow_pitch = (size_t)c->pitch * sizeof(float);
+    o->flow_pair_stride = (size_t)c->plane * sizeof(float);
+    o->width = c->W; o->height = c->H; o->batch = c->B;
+    o->halo_rows_top = c->RL * c->k;
+    o->halo_rows_bottom = c->RR * c->k;
+    return HS_OK;
+}
+
+int hs_get_timing(const hs_ctx* c, hs_timing* o) {
+    if (!c || !o) return HS_ERR_INVALID_ARG;
+    *o = c->timing;
+    return HS_OK;
+}
+
+int hs_host_alloc(void** ptr, size_t bytes) {
+    if (!ptr) return HS_ERR_INVALID_ARG;
+    *ptr = nullptr;
+    cudaError_t e = cudaMallocHost(ptr, bytes);
+    if (e != cudaSuccess) { g_create_err = cudaGetErrorString(e); return e == cudaErrorMemoryAllocation ? HS_ERR_OOM : HS_ERR_CUDA; }
+    return HS_OK;
+}
+
+int hs_host_free(void* ptr) {
+    cudaError_t e = cudaFreeHost(ptr);
+    if (e != cudaSuccess) { g_create_err = cudaGetErrorString(e); return HS_ERR_CUDA; }
+    return HS_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,475 @@
+// Horn-Schunck device kernels for sm_100a (B200).  See DESIGN.md for the data layout.
+//
+// Reference semantics: /root/reference/HornSchunckOF/hornSchunck.cpp
+//   K1  k_grad_coeff      <- getGradients :19-41 + the loop-invariant denominator of :65-66,68
+//   K2  k_jacobi_generic  <- one sweep of the hot loop :56-74, any windowSize
+//   K3  k_jacobi_tile     <- k fused sweeps of :56-74 per HBM round trip (temporal blocking)
+//   K5  k_widen / k_unpack_grad <- CV_64FC1 outputs (:49-50; plotFlow.cpp:72-75 reads double)
+//
+// Canonical arithmetic (every kernel uses exactly this, so all variants are bit-identical):
+//   row sum  h(y,x)  = ((t[x-a] + t[x-a+1]) + ...) + t[x-a+w-1]      left to right, zeros outside
+//   box sum  S(y,x)  = ((h[y-a] + h[y-a+1]) + ...) + h[y-a+w-1]      top to bottom
+//   ubar = S_u * fl(1/w^2);  vbar likewise
+//   t = fma(Ix, ubar, fma(Iy, vbar, It));  c = t * inv;  u' = fma(-Ix, c, ubar);  v' = fma(-Iy, c, vbar)
+// with inv = 1 / (fl(alpha^2) + (Ix^2 + Iy^2)) rounded once (IEEE division) in K1.
+// Explicit __f*_rn intrinsics keep the compiler from re-associating or contracting differently
+// in different kernels.
+#pragma once
+
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace hs {
+
+// Geometry shared by all kernels.  All planes of a context use the same pixel pitch.
+struct Geom {
+    int W;          // image width in pixels
+    int H;          // rows held in the buffer
+    int pitch;      // pixels per buffer row (multiple of 32)
+    long long plane;  // pixels between consecutive pairs of the batch (pitch * H)
+    int oy0, oy1;   // rows this context produces: [oy0, oy1)
+};
+
+__device__ __forceinline__ int reflect101(int i, int n) {
+    if (n == 1) return 0;
+    if (i < 0) return -i;
+    if (i >= n) return 2 * n - 2 - i;
+    return i;
+}
+
+// ------------------------------------------------------------------------------------------
+// K1: spatio-temporal gradients + per-pixel coefficients, one pass over the two uint8 frames.
+// Writes Ix,Iy as half2 (exact: |Ix|,|Iy| <= 1020 are integers), It as half (|It| <= 255) and
+// inv = 1/(alpha^2 + Ix^2 + Iy^2) as float.  4 pixels per thread, vector stores.
+// Frames: `frows` rows of `fpitch` bytes; buffer row y lives in frame row y + frow0 (frow0 = 1
+// when a seam row sits above).  BORDER_REFLECT_101 therefore only ever triggers at true image
+// borders.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_grad_coeff(const uint8_t* __restrict__ prev, const uint8_t* __restrict__ next,
+             size_t fpitch, size_t fimg, int frows, int frow0,
+             __half2* __restrict__ ixy, __half* __restrict__ itp, float* __restrict__ inv,
+             Geom g, float alpha2) {
+    const int x0 = (blockIdx.x * 32 + threadIdx.x) * 4;
+    const int y = blockIdx.y * 8 + threadIdx.y;
+    const int b = blockIdx.z;
+    if (x0 >= g.pitch || y >= g.H) return;
+    const uint8_t* P = prev + (size_t)b * fimg;
+    const uint8_t* N = next + (size_t)b * fimg;
+    const int fy = y + frow0;
+    const uint8_t* r0 = P + (size_t)reflect101(fy - 1, frows) * fpitch;
+    const uint8_t* r1 = P + (size_t)fy * fpitch;
+    const uint8_t* r2 = P + (size_t)reflect101(fy + 1, frows) * fpitch;
+    const uint8_t* n1 = N + (size_t)fy * fpitch;
+
+    // columns x0-1 .. x0+4 of the three rows (reflected at the image's left/right border)
+    int a[6], c[6], d[6];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+        int xx = x0 - 1 + i;
+        int xr = (xx < g.W + 1) ? reflect101(xx, g.W) : 0;  // columns past W+1 are never used
+        a[i] = r0[xr];
+        c[i] = r1[xr];
+        d[i] = r2[xr];
+    }
+    __half2 oxy[4];
+    __half ot[4];
+    float oinv[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int x = x0 + i;
+        int gx = 0, gy = 0, gt = 0;
+        float iv = 0.f;
+        if (x < g.W) {
+            gx = (a[i + 2] + 2 * c[i + 2] + d[i + 2]) - (a[i] + 2 * c[i] + d[i]);          // :27
+            gy = (d[i] + 2 * d[i + 1] + d[i + 2]) - (a[i] + 2 * a[i + 1] + a[i + 2]);      // :28
+            gt = (int)n1[x] - c[i + 1];                                                    // :39
+            const float den = __fadd_rn(alpha2, (float)(gx * gx + gy * gy));               // :65-68
+            iv = __fdiv_rn(1.0f, den);
+        }
+        oxy[i] = __halves2half2(__int2half_rn(gx), __int2half_rn(gy));
+        ot[i] = __int2half_rn(gt);
+        oinv[i] = iv;
+    }
+    const size_t o = (size_t)b * g.plane + (size_t)y * g.pitch + x0;
+    *reinterpret_cast<uint4*>(ixy + o) = *reinterpret_cast<uint4*>(oxy);
+    *reinterpret_cast<uint2*>(itp + o) = *reinterpret_cast<uint2*>(ot);
+    *reinterpret_cast<float4*>(inv + o) = make_float4(oinv[0], oinv[1], oinv[2], oinv[3]);
+}
+
+// ------------------------------------------------------------------------------------------
+// the per-pixel update, shared by K2 and K3 (hornSchunck.cpp:63-73)
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void hs_update(float su, float sv, float kf, float ix, float iy,
+                                          float it, float inv, float& un, float& vn) {
+    const float ub = __fmul_rn(su, kf);
+    const float vb = __fmul_rn(sv, kf);
+    const float t = __fmaf_rn(ix, ub, __fmaf_rn(iy, vb, it));
+    const float c = __fmul_rn(t, inv);
+    un = __fmaf_rn(-ix, c, ub);
+    vn = __fmaf_rn(-iy, c, vb);
+}
+
+// ------------------------------------------------------------------------------------------
+// K2: one Jacobi sweep, any window size (runtime w, anchor a).  One pixel per thread, taps read
+// through L1/L2.  This is the always-correct path (even / large windows, A/B reference for K3).
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_jacobi_generic(const float* __restrict__ u, const float* __restrict__ v,
+                 float* __restrict__ un, float* __restrict__ vn,
+                 const __half2* __restrict__ ixy, const __half* __restrict__ itp,
+                 const float* __restrict__ inv, Geom g, int w, int a, float kf) {
+    const int x = blockIdx.x * 32 + threadIdx.x;
+    const int y = g.oy0 + blockIdx.y * 8 + threadIdx.y;
+    if (x >= g.W || y >= g.oy1) return;
+    const size_t base = (size_t)blockIdx.z * g.plane;
+    const float* U = u + base;
+    const float* V = v + base;
+    float su = 0.f, sv = 0.f;
+    for (int dy = 0; dy < w; ++dy) {
+        const int yy = y + dy - a;
+        const bool yin = (yy >= 0) && (yy < g.H);
+        const size_t ro = (size_t)(yin ? yy : 0) * g.pitch;
+        float hu = 0.f, hv = 0.f;
+        for (int dx = 0; dx < w; ++dx) {
+            const int xx = x + dx - a;
+            const bool in = yin && (xx >= 0) && (xx < g.W);
+            const float tu = in ? U[ro + xx] : 0.f;
+            const float tv = in ? V[ro + xx] : 0.f;
+            hu = (dx == 0) ? tu : __fadd_rn(hu, tu);
+            hv = (dx == 0) ? tv : __fadd_rn(hv, tv);
+        }
+        su = (dy == 0) ? hu : __fadd_rn(su, hu);
+        sv = (dy == 0) ? hv : __fadd_rn(sv, hv);
+    }
+    const size_t o = base + (size_t)y * g.pitch + x;
+    const float2 xy = __half22float2(ixy[o]);
+    float nu, nv;
+    hs_update(su, sv, kf, xy.x, xy.y, __half2float(itp[o]), inv[o], nu, nv);
+    un[o] = nu;
+    vn[o] = nv;
+}
+
+// ------------------------------------------------------------------------------------------
+// TMA / mbarrier primitives (inline PTX; SASS: UTMALDG / SYNCS)
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void fence_mbar_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+                 "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(done)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+    } while (!done);
+}
+// 3-D tiled load: coordinates (x, y, pair), innermost first; out-of-bounds elements read as 0,
+// which is exactly BORDER_CONSTANT (hornSchunck.cpp:60-61) for the first fused sweep.
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar,
+                                            int x, int y, int z) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes"
+        " [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(smem_u32(dst)),
+        "l"(reinterpret_cast<uint64_t>(map)), "r"(x), "r"(y), "r"(z), "r"(smem_u32(bar))
+        : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
+}
+
+// ------------------------------------------------------------------------------------------
+// K3: k fused Jacobi sweeps per launch.
+//
+// One CTA owns a staged tile of SX x SY pixels (SX = 128 = 32 lanes x 4 px, SY = NWARP x R rows).
+// Five TMA boxes (u, v, IxIy, It, inv) land in shared memory; each thread then keeps its
+// 4 x R patch of u, v AND its coefficients in registers for all k sweeps.  Per sweep:
+//   1. row sums of the patch, horizontal neighbours by warp shuffle
+//   2. the patch's top/bottom row sums go to a double-buffered shared exchange array
+//   3. one __syncthreads
+//   4. rows of the vertical neighbours come back from shared memory, box sum, update in place
+// The ring of pixels whose dependency cone leaves the staged tile grows by (a, w/2) per sweep,
+// so after k sweeps the centre VX x VY pixels are exact and are the only ones stored.
+// Pixels outside the image must be 0 at EVERY sweep (BORDER_CONSTANT): TMA zero-fill gives that
+// for sweep 1, border tiles re-zero them after each sweep (`masked` path, CTA-uniform branch).
+// ------------------------------------------------------------------------------------------
+template <int RL, int RR, int R, int NWARP>
+struct TileShape {
+    static constexpr int SX = 128;
+    static constexpr int SY = NWARP * R;
+    static constexpr int THREADS = NWARP * 32;
+    static constexpr int EXROWS = SY + RL + RR;                       // exchange rows incl. zero pads
+    static constexpr size_t BYTES_F32 = (size_t)SX * SY * 4;
+    static constexpr size_t BYTES_F16 = (size_t)SX * SY * 2;
+    static constexpr size_t OFF_U = 0;
+    static constexpr size_t OFF_V = OFF_U + BYTES_F32;
+    static constexpr size_t OFF_IXY = OFF_V + BYTES_F32;
+    static constexpr size_t OFF_INV = OFF_IXY + BYTES_F32;
+    static constexpr size_t OFF_IT = OFF_INV + BYTES_F32;
+    static constexpr size_t OFF_EX = OFF_IT + BYTES_F16;              // [2 buf][2 field][EXROWS][SX]
+    static constexpr size_t BYTES_EX = (size_t)2 * 2 * EXROWS * SX * 4;
+    static constexpr size_t OFF_BAR = OFF_EX + BYTES_EX;
+    static constexpr size_t SMEM = OFF_BAR + 16;
+    static constexpr uint32_t TX_BYTES = (uint32_t)(4 * BYTES_F32 + BYTES_F16);
+};
+
+// row sums of one patch row: 4 outputs from 4 own values + RL left + RR right neighbours
+template <int RL, int RR>
+__device__ __forceinline__ void row_sums(const float (&a)[4], float (&h)[4]) {
+    float e[4 + RL + RR];
+#pragma unroll
+    for (int i = 0; i < RL; ++i) e[i] = __shfl_up_sync(0xffffffffu, a[4 - RL + i], 1);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) e[RL + i] = a[i];
+#pragma unroll
+    for (int i = 0; i < RR; ++i) e[RL + 4 + i] = __shfl_down_sync(0xffffffffu, a[i], 1);
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        float s = e[c];
+#pragma unroll
+        for (int d = 1; d <= RL + RR; ++d) s = __fadd_rn(s, e[c + d]);
+        h[c] = s;
+    }
+}
+
+template <int RL, int RR, int R, int NWARP, bool MASKED>
+__device__ __forceinline__ void tile_sweeps(float (&u)[R][4], float (&v)[R][4],
+                                            const float (&ix)[R][4], const float (&iy)[R][4],
+                                            const float (&it)[R][4], const float (&iv)[R][4],
+                                            float* ex, int k, float kf, int row0, int lane,
+                                            uint32_t inmask) {
+    using TS = TileShape<RL, RR, R, NWARP>;
+    for (int s = 0; s < k; ++s) {
+        float* exu = ex + (size_t)(s & 1) * 2 * TS::EXROWS * TS::SX;
+        float* exv = exu + (size_t)TS::EXROWS * TS::SX;
+        float hu[R][4], hv[R][4];
+#pragma unroll
+        for (int j = 0; j < R; ++j) {
+            row_sums<RL, RR>(u[j], hu[j]);
+            row_sums<RL, RR>(v[j], hv[j]);
+            if (j < RR || j >= R - RL) {  // rows a vertical neighbour will need
+                const int er = row0 + j + RL;
+                *reinterpret_cast<float4*>(exu + (size_t)er * TS::SX + lane * 4) =
+                    make_float4(hu[j][0], hu[j][1], hu[j][2], hu[j][3]);
+                *reinterpret_cast<float4*>(exv + (size_t)er * TS::SX + lane * 4) =
+                    make_float4(hv[j][0], hv[j][1], hv[j][2], hv[j][3]);
+            }
+        }
+        __syncthreads();
+        // neighbour rows: tile rows row0-RL .. row0-1 (above) and row0+R .. row0+R+RR-1 (below)
+        float au[RL > 0 ? RL : 1][4], av[RL > 0 ? RL : 1][4];
+        float bu[RR > 0 ? RR : 1][4], bv[RR > 0 ? RR : 1][4];
+#pragma unroll
+        for (int i = 0; i < RL; ++i) {
+            const int er = row0 - RL + i + RL;
+            const float4 q = *reinterpret_cast<const float4*>(exu + (size_t)er * TS::SX + lane * 4);
+            const float4 p = *reinterpret_cast<const float4*>(exv + (size_t)er * TS::SX + lane * 4);
+            au[i][0] = q.x; au[i][1] = q.y; au[i][2] = q.z; au[i][3] = q.w;
+            av[i][0] = p.x; av[i][1] = p.y; av[i][2] = p.z; av[i][3] = p.w;
+        }
+#pragma unroll
+        for (int i = 0; i < RR; ++i) {
+            const int er = row0 + R + i + RL;
+            const float4 q = *reinterpret_cast<const float4*>(exu + (size_t)er * TS::SX + lane * 4);
+            const float4 p = *reinterpret_cast<const float4*>(exv + (size_t)er * TS::SX + lane * 4);
+            bu[i][0] = q.x; bu[i][1] = q.y; bu[i][2] = q.z; bu[i][3] = q.w;
+            bv[i][0] = p.x; bv[i][1] = p.y; bv[i][2] = p.z; bv[i][3] = p.w;
+        }
+#pragma unroll
+        for (int j = 0; j < R; ++j) {
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                float su = 0.f, sv = 0.f;
+#pragma unroll
+                for (int d = -RL; d <= RR; ++d) {
+                    const int i = j + d;  // patch-relative row of this tap
+                    float tu, tv;
+                    if (i < 0) { tu = au[i + RL][c]; tv = av[i + RL][c]; }
+                    else if (i >= R) { tu = bu[i - R][c]; tv = bv[i - R][c]; }
+                    else { tu = hu[i][c]; tv = hv[i][c]; }
+                    su = (d == -RL) ? tu : __fadd_rn(su, tu);
+                    sv = (d == -RL) ? tv : __fadd_rn(sv, tv);
+                }
+                float nu, nv;
+                hs_update(su, sv, kf, ix[j][c], iy[j][c], it[j][c], iv[j][c], nu, nv);
+                if (MASKED) {
+                    const bool in = (inmask >> (j * 4 + c)) & 1u;
+                    nu = in ? nu : 0.f;
+                    nv = in ? nv : 0.f;
+                }
+                u[j][c] = nu;
+                v[j][c] = nv;
+            }
+        }
+    }
+}
+
+template <int RL, int RR, int R, int NWARP>
+__global__ void __launch_bounds__(NWARP * 32, 1)
+k_jacobi_tile(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CUtensorMap tm_v,
+              const __grid_constant__ CUtensorMap tm_ixy, const __grid_constant__ CUtensorMap tm_it,
+              const __grid_constant__ CUtensorMap tm_inv,
+              float* __restrict__ un, float* __restrict__ vn, Geom g,
+              int k, int hxl, int hyt, int vx, int vy, float kf) {
+    using TS = TileShape<RL, RR, R, NWARP>;
+    static_assert(R * 4 <= 32, "in-image mask is one 32-bit word per thread");
+    static_assert(RL <= 4 && RR <= 4, "horizontal neighbours come from the adjacent lane only");
+    extern __shared__ __align__(128) unsigned char smem[];
+    float* s_u = reinterpret_cast<float*>(smem + TS::OFF_U);
+    float* s_v = reinterpret_cast<float*>(smem + TS::OFF_V);
+    __half2* s_ixy = reinterpret_cast<__half2*>(smem + TS::OFF_IXY);
+    float* s_inv = reinterpret_cast<float*>(smem + TS::OFF_INV);
+    __half* s_it = reinterpret_cast<__half*>(smem + TS::OFF_IT);
+    float* s_ex = reinterpret_cast<float*>(smem + TS::OFF_EX);
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem + TS::OFF_BAR);
+
+    const int tid = threadIdx.x;
+    const int lane = tid & 31;
+    const int warp = tid >> 5;
+    const int b = blockIdx.z;
+    const int tx0 = blockIdx.x * vx - hxl;            // staged tile origin (may be negative)
+    const int ty0 = g.oy0 + blockIdx.y * vy - hyt;
+
+    if (tid == 0) {
+        tma_prefetch_desc(&tm_u);
+        tma_prefetch_desc(&tm_v);
+        tma_prefetch_desc(&tm_ixy);
+        tma_prefetch_desc(&tm_it);
+        tma_prefetch_desc(&tm_inv);
+        mbar_init(bar, 1);
+        fence_mbar_init();
+    }
+    __syncthreads();
+    if (tid == 0) {
+        mbar_expect_tx(bar, TS::TX_BYTES);
+        tma_load_3d(s_u, &tm_u, bar, tx0, ty0, b);
+        tma_load_3d(s_v, &tm_v, bar, tx0, ty0, b);
+        tma_load_3d(s_ixy, &tm_ixy, bar, tx0, ty0, b);
+        tma_load_3d(s_inv, &tm_inv, bar, tx0, ty0, b);
+        tma_load_3d(s_it, &tm_it, bar, tx0, ty0, b);
+    }
+    // while the boxes are in flight: zero the exchange pad rows (above row 0 / below row SY-1)
+    for (int i = tid; i < 2 * 2 * (RL + RR) * TS::SX; i += TS::THREADS) {
+        const int col = i % TS::SX;
+        const int pr = (i / TS::SX) % (RL + RR);
+        const int fb = i / (TS::SX * (RL + RR));      // buf*2 + field
+        const int er = (pr < RL) ? pr : (TS::SY + RL + (pr - RL));
+        s_ex[((size_t)fb * TS::EXROWS + er) * TS::SX + col] = 0.f;
+    }
+
+    const int row0 = warp * R;                        // first tile row of this thread's patch
+    const int gx0 = tx0 + lane * 4;
+    const int gy0 = ty0 + row0;
+    // which of the patch pixels lie inside the image (bit j*4+c)
+    uint32_t inmask = 0;
+#pragma unroll
+    for (int j = 0; j < R; ++j)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            const bool in = (gy0 + j >= 0) && (gy0 + j < g.H) && (gx0 + c >= 0) && (gx0 + c < g.W);
+            inmask |= (in ? 1u : 0u) << (j * 4 + c);
+        }
+    const bool tile_inside = (tx0 >= 0) && (tx0 + TS::SX <= g.W) && (ty0 >= 0) && (ty0 + TS::SY <= g.H);
+
+    mbar_wait(bar, 0);
+
+    float u[R][4], v[R][4], ix[R][4], iy[R][4], it[R][4], iv[R][4];
+#pragma unroll
+    for (int j = 0; j < R; ++j) {
+        const int so = (row0 + j) * TS::SX + lane * 4;
+        const float4 qu = *reinterpret_cast<const float4*>(s_u + so);
+        const float4 qv = *reinterpret_cast<const float4*>(s_v + so);
+        const float4 qi = *reinterpret_cast<const float4*>(s_inv + so);
+        const uint4 qxy = *reinterpret_cast<const uint4*>(s_ixy + so);
+        const uint2 qt = *reinterpret_cast<const uint2*>(s_it + so);
+        u[j][0] = qu.x; u[j][1] = qu.y; u[j][2] = qu.z; u[j][3] = qu.w;
+        v[j][0] = qv.x; v[j][1] = qv.y; v[j][2] = qv.z; v[j][3] = qv.w;
+        iv[j][0] = qi.x; iv[j][1] = qi.y; iv[j][2] = qi.z; iv[j][3] = qi.w;
+        const uint32_t wxy[4] = {qxy.x, qxy.y, qxy.z, qxy.w};
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&wxy[c]));
+            ix[j][c] = f.x;
+            iy[j][c] = f.y;
+        }
+        const float2 t01 = __half22float2(*reinterpret_cast<const __half2*>(&qt.x));
+        const float2 t23 = __half22float2(*reinterpret_cast<const __half2*>(&qt.y));
+        it[j][0] = t01.x; it[j][1] = t01.y; it[j][2] = t23.x; it[j][3] = t23.y;
+    }
+    __syncthreads();  // exchange pad rows are zeroed before anyone reads them
+
+    if (tile_inside)
+        tile_sweeps<RL, RR, R, NWARP, false>(u, v, ix, iy, it, iv, s_ex, k, kf, row0, lane, inmask);
+    else
+        tile_sweeps<RL, RR, R, NWARP, true>(u, v, ix, iy, it, iv, s_ex, k, kf, row0, lane, inmask);
+
+    // store the exact centre of the tile
+    const int lx = lane * 4;
+    if (lx >= hxl && lx < hxl + vx && gx0 < g.W) {
+        float* U = un + (size_t)b * g.plane;
+        float* V = vn + (size_t)b * g.plane;
+#pragma unroll
+        for (int j = 0; j < R; ++j) {
+            const int ly = row0 + j;
+            const int gy = gy0 + j;
+            if (ly >= hyt && ly < hyt + vy && gy < g.oy1) {
+                const size_t o = (size_t)gy * g.pitch + gx0;
+                *reinterpret_cast<float4*>(U + o) = make_float4(u[j][0], u[j][1], u[j][2], u[j][3]);
+                *reinterpret_cast<float4*>(V + o) = make_float4(v[j][0], v[j][1], v[j][2], v[j][3]);
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// K5: outputs.  fp32 planes -> fp32/fp64 dense-ish host layout staging (pitch kept), and the
+// gradient planes back out of the packed coefficient layout.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_widen(const float* __restrict__ a, const float* __restrict__ b2, double* __restrict__ oa,
+        double* __restrict__ ob, long long n) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long p = i; p < n; p += stride) {
+        oa[p] = (double)a[p];
+        ob[p] = (double)b2[p];
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+k_unpack_grad(const __half2* __restrict__ ixy, const __half* __restrict__ itp, T* __restrict__ gx,
+              T* __restrict__ gy, T* __restrict__ gt, long long n) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long p = i; p < n; p += stride) {
+        const float2 f = __half22float2(ixy[p]);
+        gx[p] = (T)f.x;
+        gy[p] = (T)f.y;
+        gt[p] = (T)__half2float(itp[p]);
+    }
+}
+
+}  // namespace hs

@@ -1,0 +1,210 @@
+"""Host-side mirror of the reference interface, on top of the C ABI (include/hs.h).
+
+`hornSchunck` keeps the name, constructor arguments, public fields and method names of
+class hornSchunck in /root/reference/HornSchunckOF/hornSchunck.cpp:8-76 so the parity tests read
+like the reference's call site (main.cpp:97-98).  `Solver` is the thin RAII wrapper around one
+hs_ctx that the bench and the row-slab driver use.  All arithmetic happens in libhs_b200.so.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import hs_ctypes as H
+
+
+def _as_u8_image(img: np.ndarray, name: str) -> np.ndarray:
+    a = np.asarray(img)
+    if a.ndim != 2:
+        raise ValueError(f"{name}: expected a single-channel 2-D image, got shape {a.shape} "
+                         "(convert colour frames first, main.cpp:11-26)")
+    if a.dtype != np.uint8:
+        # the reference converts any depth to CV_64F (:23-24); the device path takes 8-bit frames,
+        # so accept other dtypes only when the conversion is lossless
+        b = a.astype(np.uint8)
+        if not np.array_equal(b.astype(a.dtype), a):
+            raise ValueError(f"{name}: dtype {a.dtype} holds values that are not 8-bit integers")
+        a = b
+    if a.strides[1] != 1:
+        a = np.ascontiguousarray(a)
+    return a
+
+
+class Solver:
+    """One hs_ctx: fixed geometry and parameters, reusable across frame pairs."""
+
+    def __init__(self, width, height, window_size, max_iterations, alpha, batch=1, device=-1,
+                 temporal_k=0, flags=0, out_rows=None, stream=None):
+        self._lib = H.load_library()
+        cfg = H.HsConfig()
+        cfg.struct_size = C.sizeof(H.HsConfig)
+        cfg.width, cfg.height = int(width), int(height)
+        cfg.window_size, cfg.max_iterations = int(window_size), int(max_iterations)
+        cfg.alpha = float(alpha)
+        cfg.batch, cfg.device, cfg.temporal_k, cfg.flags = int(batch), int(device), int(temporal_k), int(flags)
+        if out_rows is not None:
+            cfg.out_row_begin, cfg.out_row_end = int(out_rows[0]), int(out_rows[1])
+        cfg.stream = stream
+        self._ctx = C.c_void_p()
+        rc = self._lib.hs_create(C.byref(cfg), C.byref(self._ctx))
+        if rc != H.HS_OK:
+            self._ctx = None
+            raise H.HsError(rc, (self._lib.hs_last_error(None) or b"").decode())
+        self.width, self.height, self.batch = cfg.width, cfg.height, max(1, cfg.batch)
+        self.out_rows = (cfg.out_row_begin, cfg.out_row_end) if out_rows is not None else (0, cfg.height)
+        self.flags = cfg.flags
+        self.frame_rows = cfg.height + (1 if cfg.flags & H.FLAG_TOP_IS_SEAM else 0) + \
+            (1 if cfg.flags & H.FLAG_BOTTOM_IS_SEAM else 0)
+
+    # -- plumbing ---------------------------------------------------------------------------
+    def _check(self, rc):
+        if rc != H.HS_OK:
+            raise H.HsError(rc, (self._lib.hs_last_error(self._ctx) or b"").decode())
+
+    def close(self):
+        if getattr(self, "_ctx", None):
+            self._lib.hs_destroy(self._ctx)
+            self._ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def _frames(self, prev, nxt):
+        """-> (prev, next, row strides, image strides) for (H, W) or (B, H, W) uint8 input."""
+        if self.batch == 1 and np.asarray(prev).ndim == 2:
+            p, n = _as_u8_image(prev, "prev"), _as_u8_image(nxt, "next")
+            shape = p.shape
+            ps, ns, pis, nis = p.strides[0], n.strides[0], 0, 0
+        else:
+            p = np.ascontiguousarray(prev, dtype=np.uint8)
+            n = np.ascontiguousarray(nxt, dtype=np.uint8)
+            if p.ndim != 3 or p.shape[0] != self.batch:
+                raise ValueError(f"expected {self.batch} frames, got shape {p.shape}")
+            shape = p.shape[1:]
+            ps, ns, pis, nis = p.strides[1], n.strides[1], p.strides[0], n.strides[0]
+        if p.shape != n.shape:
+            raise ValueError("Image sizes are different. Please provide images of same size.")  # main.cpp:70-73
+        if shape != (self.frame_rows, self.width):
+            raise ValueError(f"frames are {shape}, context was created for {(self.frame_rows, self.width)}")
+        return p, n, ps, ns, pis, nis
+
+    def _outputs(self, dtype):
+        dtype = np.dtype(dtype)
+        if dtype not in (np.dtype(np.float32), np.dtype(np.float64)):
+            raise ValueError("out dtype must be float32 or float64")
+        rows = self.out_rows[1] - self.out_rows[0]
+        shape = (rows, self.width) if self.batch == 1 else (self.batch, rows, self.width)
+        return np.empty(shape, dtype), np.empty(shape, dtype), (H.HS_F64 if dtype == np.float64 else H.HS_F32)
+
+    # -- the reference's two methods ---------------------------------------------------------
+    def solve(self, prev, nxt, out_dtype=np.float64):
+        """getFlow (hornSchunck.cpp:43-75): host uint8 frames -> host (u, v)."""
+        p, n, ps, ns, pis, nis = self._frames(prev, nxt)
+        u, v, dt = self._outputs(out_dtype)
+        rs = u.strides[-2]
+        ims = u.strides[0] if self.batch > 1 else 0
+        self._check(self._lib.hs_solve(self._ctx, p.ctypes.data, ps, pis, n.ctypes.data, ns, nis,
+                                       u.ctypes.data, rs, ims, v.ctypes.data, rs, ims, dt))
+        return u, v
+
+    def gradients(self, prev, nxt, out_dtype=np.float64):
+        """getGradients (hornSchunck.cpp:19-41): -> (gradX, gradY, gradT)."""
+        p, n, ps, ns, _, _ = self._frames(prev, nxt)
+        dtype = np.dtype(out_dtype)
+        rows = self.out_rows[1] - self.out_rows[0]
+        g = [np.empty((rows, self.width), dtype) for _ in range(3)]
+        dt = H.HS_F64 if dtype == np.float64 else H.HS_F32
+        self._check(self._lib.hs_gradients(self._ctx, p.ctypes.data, ps, n.ctypes.data, ns,
+                                           g[0].ctypes.data, g[1].ctypes.data, g[2].ctypes.data,
+                                           g[0].strides[0], dt))
+        return tuple(g)
+
+    # -- device-resident pipeline -------------------------------------------------------------
+    def upload(self, prev, nxt):
+        p, n, ps, ns, pis, nis = self._frames(prev, nxt)
+        self._check(self._lib.hs_upload(self._ctx, p.ctypes.data, ps, pis, n.ctypes.data, ns, nis))
+        self._keep = (p, n)   # the copy is asynchronous for pinned memory: keep the arrays alive
+
+    def upload_raw(self, prev_ptr, prev_row_stride, prev_img_stride, next_ptr, next_row_stride, next_img_stride):
+        self._check(self._lib.hs_upload(self._ctx, prev_ptr, prev_row_stride, prev_img_stride,
+                                        next_ptr, next_row_stride, next_img_stride))
+
+    def prepare(self):
+        self._check(self._lib.hs_prepare(self._ctx))
+
+    def iterate(self, iterations):
+        self._check(self._lib.hs_iterate(self._ctx, int(iterations)))
+
+    def solve_device(self):
+        self._check(self._lib.hs_solve_device(self._ctx))
+
+    def sync(self):
+        self._check(self._lib.hs_sync(self._ctx))
+
+    def download(self, out_dtype=np.float64):
+        u, v, dt = self._outputs(out_dtype)
+        rs = u.strides[-2]
+        ims = u.strides[0] if self.batch > 1 else 0
+        self._check(self._lib.hs_download(self._ctx, u.ctypes.data, rs, ims, v.ctypes.data, rs, ims, dt))
+        return u, v
+
+    def download_raw(self, u_ptr, v_ptr, row_stride, img_stride, dt):
+        self._check(self._lib.hs_download(self._ctx, u_ptr, row_stride, img_stride, v_ptr, row_stride, img_stride, dt))
+
+    def device_view(self) -> H.HsDeviceView:
+        view = H.HsDeviceView()
+        self._check(self._lib.hs_get_device_view(self._ctx, C.byref(view)))
+        return view
+
+    def timing(self) -> H.HsTiming:
+        t = H.HsTiming()
+        self._check(self._lib.hs_get_timing(self._ctx, C.byref(t)))
+        return t
+
+
+class hornSchunck:  # noqa: N801 - the reference's class name (hornSchunck.cpp:8)
+    """Drop-in for `hornSchunck hs(windowSize, maxIterations, alpha); hs.getFlow(prev, next, u, v);`
+    (main.cpp:97-98).  C++ out-parameters become return values; outputs are float64 H x W arrays,
+    freshly allocated, like the CV_64FC1 Mats of the reference."""
+
+    def __init__(self, inpWindowSize, inpMaxIterations, inpAlpha, device=-1):
+        self.windowSize = int(inpWindowSize)        # :14
+        self.maxIterations = int(inpMaxIterations)  # :15
+        self.alpha = float(inpAlpha)                # :16
+        self._device = device
+        self._solver = None
+        self._key = None
+
+    def _ctx_for(self, shape):
+        key = (shape, self.windowSize, self.maxIterations, self.alpha)
+        if key != self._key:
+            if self._solver is not None:
+                self._solver.close()
+            self._solver = Solver(shape[1], shape[0], self.windowSize, self.maxIterations, self.alpha,
+                                  device=self._device)
+            self._key = key
+        return self._solver
+
+    def getGradients(self, imagePrev, imageNext):   # noqa: N802,N803
+        p = _as_u8_image(imagePrev, "imagePrev")
+        return self._ctx_for(p.shape).gradients(p, imageNext, np.float64)
+
+    def getFlow(self, imagePrev, imageNext):        # noqa: N802,N803
+        p = _as_u8_image(imagePrev, "imagePrev")
+        return self._ctx_for(p.shape).solve(p, imageNext, np.float64)
+
+    def close(self):
+        if self._solver is not None:
+            self._solver.close()
+            self._solver = None
+            self._key = None

@@ -1,0 +1,91 @@
+"""ctypes binding of include/hs.h - the same symbols the C++ adapter (adapter/hornSchunck.cpp)
+calls.  Nothing here computes anything: every call goes to libhs_b200.so (CUDA, sm_100a)."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+from . import _build
+
+HS_OK = 0
+HS_F32, HS_F64 = 0, 1
+FLAG_TOP_IS_SEAM, FLAG_BOTTOM_IS_SEAM, FLAG_FORCE_GENERIC, FLAG_NO_GRAPH = 1, 2, 4, 8
+
+STATUS_NAMES = {0: "HS_OK", 1: "HS_ERR_INVALID_ARG", 2: "HS_ERR_CUDA", 3: "HS_ERR_OOM",
+                4: "HS_ERR_UNSUPPORTED", 5: "HS_ERR_STATE"}
+
+# every extern "C" symbol include/hs.h declares (tests check the library exports all of them)
+SYMBOLS = ["hs_create", "hs_destroy", "hs_solve", "hs_gradients", "hs_upload", "hs_prepare",
+           "hs_iterate", "hs_solve_device", "hs_download", "hs_sync", "hs_get_device_view",
+           "hs_get_timing", "hs_last_error", "hs_version", "hs_host_alloc", "hs_host_free"]
+
+
+class HsConfig(C.Structure):
+    _fields_ = [("struct_size", C.c_uint32), ("width", C.c_int32), ("height", C.c_int32),
+                ("window_size", C.c_int32), ("max_iterations", C.c_int32), ("alpha", C.c_double),
+                ("batch", C.c_int32), ("device", C.c_int32), ("temporal_k", C.c_int32),
+                ("flags", C.c_uint32), ("out_row_begin", C.c_int32), ("out_row_end", C.c_int32),
+                ("stream", C.c_void_p)]
+
+
+class HsTiming(C.Structure):
+    _fields_ = [("h2d_ms", C.c_float), ("prepare_ms", C.c_float), ("iterate_ms", C.c_float),
+                ("d2h_ms", C.c_float), ("total_ms", C.c_float), ("launches", C.c_int32),
+                ("temporal_k", C.c_int32), ("kernel_id", C.c_int32)]
+
+
+class HsDeviceView(C.Structure):
+    _fields_ = [("prev", C.c_void_p), ("next", C.c_void_p), ("frame_pitch", C.c_size_t),
+                ("frame_pair_stride", C.c_size_t), ("frame_rows", C.c_int32), ("frame_row0", C.c_int32),
+                ("u", C.c_void_p), ("v", C.c_void_p), ("flow_pitch", C.c_size_t),
+                ("flow_pair_stride", C.c_size_t), ("width", C.c_int32), ("height", C.c_int32),
+                ("batch", C.c_int32), ("halo_rows_top", C.c_int32), ("halo_rows_bottom", C.c_int32)]
+
+
+class HsError(RuntimeError):
+    def __init__(self, status: int, message: str):
+        super().__init__(f"{STATUS_NAMES.get(status, status)}: {message}")
+        self.status = status
+
+
+_lib = None
+
+
+def load_library(path: str | None = None):
+    """dlopen libhs_b200.so (building it first if nvcc is here and it is stale).  Raises if the
+    library cannot be had: there is deliberately no fallback implementation."""
+    global _lib
+    if _lib is not None and path is None:
+        return _lib
+    if path is None:
+        path = _build.LIB
+        if _build.is_stale() and _build.nvcc_path():
+            _build.build()
+    if not os.path.exists(path):
+        raise RuntimeError(f"{path} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'`"
+                           " (the CUDA library is the only implementation; there is no CPU fallback)")
+    lib = C.CDLL(path)
+    vp, sz, i32 = C.c_void_p, C.c_size_t, C.c_int
+    lib.hs_create.argtypes = [C.POINTER(HsConfig), C.POINTER(vp)]
+    lib.hs_destroy.argtypes = [vp]
+    lib.hs_destroy.restype = None
+    lib.hs_solve.argtypes = [vp, vp, sz, sz, vp, sz, sz, vp, sz, sz, vp, sz, sz, i32]
+    lib.hs_gradients.argtypes = [vp, vp, sz, vp, sz, vp, vp, vp, sz, i32]
+    lib.hs_upload.argtypes = [vp, vp, sz, sz, vp, sz, sz]
+    lib.hs_prepare.argtypes = [vp]
+    lib.hs_iterate.argtypes = [vp, i32]
+    lib.hs_solve_device.argtypes = [vp]
+    lib.hs_download.argtypes = [vp, vp, sz, sz, vp, sz, sz, i32]
+    lib.hs_sync.argtypes = [vp]
+    lib.hs_get_device_view.argtypes = [vp, C.POINTER(HsDeviceView)]
+    lib.hs_get_timing.argtypes = [vp, C.POINTER(HsTiming)]
+    lib.hs_last_error.argtypes = [vp]
+    lib.hs_last_error.restype = C.c_char_p
+    lib.hs_version.argtypes = []
+    lib.hs_host_alloc.argtypes = [C.POINTER(vp), sz]
+    lib.hs_host_free.argtypes = [vp]
+    for name in SYMBOLS:
+        if name not in ("hs_destroy", "hs_last_error"):
+            getattr(lib, name).restype = i32
+    _lib = lib
+    return lib

@@ -1,0 +1,166 @@
+/*
+ * hs.h - C ABI of the B200-native Horn-Schunck solver (libhs_b200.so).
+ *
+ * This is the drop-in boundary for the one hot path of liuyang9609/Cpp-Optical-Flow:
+ *     class hornSchunck            HornSchunckOF/hornSchunck.cpp:8-76
+ *     call site                    HornSchunckOF/main.cpp:97-98
+ * The reference has no FFI layer of its own (the class is #included textually, main.cpp:8);
+ * the entry points below are what a binding for that class has to reach, one per public
+ * member plus the device-resident / row-slab helpers the multi-GPU host code needs.
+ * cpp-optical-flow_b200/adapter/hornSchunck.cpp is the header-only cv::Mat adapter with the
+ * reference's class surface; cpp-optical-flow_b200/hs_ctypes.py binds the same symbols from
+ * Python (INTEGRATION.md shows both).
+ *
+ * Conventions
+ *   - plain C, no CUDA/torch/OpenCV types; every pointer is a raw host or device address
+ *   - every function returns an hs_status (HS_OK == 0) and never throws; the text of the last
+ *     failure is available from hs_last_error(ctx) (or hs_last_error(NULL) for hs_create)
+ *   - a context is bound to one CUDA device and must not be used from two threads at once;
+ *     distinct contexts are independent; there is no global mutable state
+ *   - there is NO CPU fallback: without a usable CUDA device hs_create fails with HS_ERR_CUDA
+ *   - images are row-major with a byte stride ("step" of cv::Mat); strides may exceed the row
+ *
+ * Semantics (identical to the reference for the same windowSize / maxIterations / alpha):
+ *   gradX, gradY = unnormalised 3x3 Sobel of the PREVIOUS frame, BORDER_REFLECT_101  (:27-28)
+ *   gradT        = next - prev                                                     (:39)
+ *   per sweep    ubar = w x w box mean of u incl. centre, zero padding, anchor w-w/2-1 (:53-54,60)
+ *                c = (gradX*ubar + gradY*vbar + gradT) / (alpha^2 + gradX^2 + gradY^2)  (:63-68)
+ *                u = ubar - gradX*c,  v = vbar - gradY*c   (Jacobi, both from old averages) (:69-73)
+ *   u = v = 0 initially (:49-50), exactly maxIterations sweeps, no convergence test (:56).
+ * Arithmetic is fp32 on the device (gradients are exact integers); outputs are widened to fp64
+ * on request because the reference's consumers read u.at<double> (plotFlow.cpp:72-75).
+ */
+#ifndef HS_B200_H
+#define HS_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HS_VERSION 100 /* 0.1.0 */
+
+typedef enum hs_status {
+    HS_OK = 0,
+    HS_ERR_INVALID_ARG = 1,
+    HS_ERR_CUDA = 2,
+    HS_ERR_OOM = 3,
+    HS_ERR_UNSUPPORTED = 4,
+    HS_ERR_STATE = 5 /* call order violated, e.g. iterate before prepare */
+} hs_status;
+
+typedef enum hs_dtype { HS_F32 = 0, HS_F64 = 1 } hs_dtype;
+
+/* hs_config.flags */
+#define HS_FLAG_TOP_IS_SEAM 0x1    /* row-slab: rows exist above this context's buffer          */
+#define HS_FLAG_BOTTOM_IS_SEAM 0x2 /* row-slab: rows exist below this context's buffer          */
+#define HS_FLAG_FORCE_GENERIC 0x4  /* always use the one-sweep-per-launch kernel (A/B testing)  */
+#define HS_FLAG_NO_GRAPH 0x8       /* do not capture the sweep loop into a CUDA graph           */
+
+/*
+ * Replaces the three public fields + constructor of class hornSchunck (hornSchunck.cpp:10-17)
+ * and adds the geometry the C++ code reads off cv::Mat.  Zero-initialise, set struct_size =
+ * sizeof(hs_config), then fill what you need; 0 means "default" for every optional field.
+ */
+typedef struct hs_config {
+    uint32_t struct_size;
+    int32_t width;          /* columns of each frame                                   (required) */
+    int32_t height;         /* rows held by this context (whole image, or slab + halo) (required) */
+    int32_t window_size;    /* windowSize  (hornSchunck.cpp:10,14), any w >= 1         (required) */
+    int32_t max_iterations; /* maxIterations (:10,15), >= 0                            (required) */
+    double alpha;           /* alpha (:11,16); 0 is legal and yields IEEE nan/inf like upstream   */
+    int32_t batch;          /* independent frame pairs solved per call (default 1)                */
+    int32_t device;         /* CUDA ordinal; -1 = current device                                  */
+    int32_t temporal_k;     /* sweeps fused per launch (temporal blocking); 0 = auto              */
+    uint32_t flags;         /* HS_FLAG_*                                                          */
+    /* Row-slab decomposition (one context per GPU).  The context's buffer holds `height` rows of
+     * a taller image; it produces rows [out_row_begin, out_row_end) and treats the other rows as
+     * halo that the host refreshes between hs_iterate calls.  0/0 = the whole buffer. */
+    int32_t out_row_begin;
+    int32_t out_row_end;
+    void* stream;           /* cudaStream_t to run on; NULL = a private non-blocking stream       */
+} hs_config;
+
+typedef struct hs_ctx hs_ctx;
+
+/* cudaEvent-measured milliseconds of the last hs_solve / hs_gradients call. */
+typedef struct hs_timing {
+    float h2d_ms;
+    float prepare_ms; /* gradient + coefficient stage                    */
+    float iterate_ms; /* all Jacobi sweeps                               */
+    float d2h_ms;     /* widen + device->host                            */
+    float total_ms;
+    int32_t launches;   /* kernels launched by the last call              */
+    int32_t temporal_k; /* fused sweeps per launch actually used          */
+    int32_t kernel_id;  /* 0 = generic one-sweep kernel, 1 = fused tile kernel */
+} hs_timing;
+
+/* Device-side view used by device-resident callers (bench, row-slab host code). All pointers
+ * are device addresses owned by the context and stay valid until hs_destroy. */
+typedef struct hs_device_view {
+    void* prev;           /* uint8, frame_pitch bytes per row; rows = height + seam rows          */
+    void* next;
+    size_t frame_pitch;   /* bytes                                                                */
+    size_t frame_pair_stride; /* bytes between consecutive pairs of the batch                     */
+    int32_t frame_rows;   /* height + (top seam ? 1 : 0) + (bottom seam ? 1 : 0)                  */
+    int32_t frame_row0;   /* buffer row of the context's row 0 inside prev/next (0 or 1)          */
+    float* u;             /* CURRENT flow planes (they ping-pong: re-query after hs_iterate)       */
+    float* v;
+    size_t flow_pitch;    /* bytes per row of u / v                                               */
+    size_t flow_pair_stride; /* bytes between pairs                                               */
+    int32_t width, height, batch;
+    int32_t halo_rows_top;    /* rows of halo a neighbour must refresh per fused launch: a*k      */
+    int32_t halo_rows_bottom; /* (w/2)*k                                                          */
+} hs_device_view;
+
+/* ---- lifetime -------------------------------------------------------------------------- */
+/* hornSchunck::hornSchunck(int,int,double)  hornSchunck.cpp:13-17 (+ geometry). */
+int hs_create(const hs_config* cfg, hs_ctx** out);
+void hs_destroy(hs_ctx* ctx);
+
+/* ---- the reference's two public methods --------------------------------------------------- */
+/* hornSchunck::getFlow  hornSchunck.cpp:43-75 / main.cpp:98.  prev/next: host uint8, `batch`
+ * images each (image i starts at prev + i*prev_image_stride bytes; pass 0 for batch == 1).
+ * u/v: host outputs of out_dtype, same batching rule.  Synchronous. */
+int hs_solve(hs_ctx* ctx,
+             const uint8_t* prev, size_t prev_row_stride, size_t prev_image_stride,
+             const uint8_t* next, size_t next_row_stride, size_t next_image_stride,
+             void* u, size_t u_row_stride, size_t u_image_stride,
+             void* v, size_t v_row_stride, size_t v_image_stride,
+             int out_dtype);
+
+/* hornSchunck::getGradients  hornSchunck.cpp:19-41.  gx/gy/gt: host outputs of out_dtype, all
+ * with the same row stride (batch == 1 contexts only). */
+int hs_gradients(hs_ctx* ctx,
+                 const uint8_t* prev, size_t prev_row_stride,
+                 const uint8_t* next, size_t next_row_stride,
+                 void* gx, void* gy, void* gt, size_t out_row_stride, int out_dtype);
+
+/* ---- device-resident pipeline (what hs_solve is made of) ------------------------------------ */
+int hs_upload(hs_ctx* ctx,                                    /* host uint8 -> device frames     */
+              const uint8_t* prev, size_t prev_row_stride, size_t prev_image_stride,
+              const uint8_t* next, size_t next_row_stride, size_t next_image_stride);
+int hs_prepare(hs_ctx* ctx);                                  /* gradients+coefficients, u=v=0   */
+int hs_iterate(hs_ctx* ctx, int iterations);                  /* `iterations` more Jacobi sweeps */
+int hs_solve_device(hs_ctx* ctx);                             /* prepare + iterate(max_iterations)*/
+int hs_download(hs_ctx* ctx,                                  /* device u,v -> host              */
+                void* u, size_t u_row_stride, size_t u_image_stride,
+                void* v, size_t v_row_stride, size_t v_image_stride, int out_dtype);
+int hs_sync(hs_ctx* ctx);                                     /* wait for the context's stream   */
+int hs_get_device_view(hs_ctx* ctx, hs_device_view* out);
+
+/* ---- introspection --------------------------------------------------------------------------- */
+int hs_get_timing(const hs_ctx* ctx, hs_timing* out);
+const char* hs_last_error(const hs_ctx* ctx); /* ctx may be NULL: last hs_create failure of thread */
+int hs_version(void);
+
+/* Pinned host memory for callers that want zero-copy-speed transfers (optional). */
+int hs_host_alloc(void** ptr, size_t bytes);
+int hs_host_free(void* ptr);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HS_B200_H */
