@@ -58,13 +58,12 @@ struct hs_ctx {
     float* d_u[2] = {nullptr, nullptr};
     float* d_v[2] = {nullptr, nullptr};
     int cur = 0;
-    __half2* d_ixy = nullptr;
-    __half* d_it = nullptr;
+    uint32_t* d_cpk = nullptr;   // packed {Ix, Iy, It}
     float* d_inv = nullptr;
     void* d_out = nullptr;
     size_t out_bytes = 0;
 
-    CUtensorMap tm_u[2], tm_v[2], tm_ixy, tm_it, tm_inv;
+    CUtensorMap tm_u[2], tm_v[2], tm_cpk, tm_inv;
     int kernel_id = 0;  // 0 generic, 1 fused tile
     int k = 1;
 
@@ -130,6 +129,11 @@ int make_map(hs_ctx* c, CUtensorMap* m, void* base, CUtensorMapDataType dt, int 
     return HS_OK;
 }
 
+int env_int(const char* name, int dflt) {
+    const char* s = getenv(name);
+    return (s && *s) ? atoi(s) : dflt;
+}
+
 template <int RL, int RR>
 struct Tile {
     using TS = hs::TileShape<RL, RR, TILE_R, TILE_NWARP>;
@@ -145,7 +149,7 @@ struct Tile {
         dim3 grid((c->W + vx - 1) / vx, (c->oy1 - c->oy0 + vy - 1) / vy, c->B);
         const float kf = 1.0f / (float)(c->w * c->w);
         kernel()<<<grid, TS::THREADS, TS::SMEM, c->stream>>>(
-            c->tm_u[c->cur], c->tm_v[c->cur], c->tm_ixy, c->tm_it, c->tm_inv, c->d_u[c->cur ^ 1],
+            c->tm_u[c->cur], c->tm_v[c->cur], c->tm_cpk, c->tm_inv, c->d_u[c->cur ^ 1],
             c->d_v[c->cur ^ 1], c->geom(), kk, hxl, hyt, vx, vy, kf);
         return cudaGetLastError();
     }
@@ -161,10 +165,6 @@ bool tile_dispatch(int RL, int RR, F&& f) {
     return false;
 }
 
-int env_int(const char* name, int dflt) {
-    const char* s = getenv(name);
-    return (s && *s) ? atoi(s) : dflt;
-}
 
 int ensure_out(hs_ctx* c, size_t bytes) {
     if (c->out_bytes >= bytes) return HS_OK;
@@ -212,7 +212,7 @@ int do_prepare(hs_ctx* c) {
     dim3 grid((c->pitch / 4 + 31) / 32, (c->H + 7) / 8, c->B);
     const float a2 = (float)(c->alpha * c->alpha);
     hs::k_grad_coeff<<<grid, block, 0, c->stream>>>(c->d_prev, c->d_next, c->fpitch, c->fimg, c->frows,
-                                                    c->frow0, c->d_ixy, c->d_it, c->d_inv, c->geom(), a2);
+                                                    c->frow0, c->d_cpk, c->d_inv, c->geom(), a2);
     HS_CUDA(c, cudaGetLastError());
     c->timing.launches += 1;
     c->prepared = true;
@@ -234,7 +234,7 @@ int do_iterate(hs_ctx* c, int iters) {
             dim3 grid((c->W + 31) / 32, (c->oy1 - c->oy0 + 7) / 8, c->B);
             const float kf = 1.0f / (float)(c->w * c->w);
             hs::k_jacobi_generic<<<grid, block, 0, c->stream>>>(c->d_u[c->cur], c->d_v[c->cur], c->d_u[c->cur ^ 1],
-                                                                c->d_v[c->cur ^ 1], c->d_ixy, c->d_it, c->d_inv,
+                                                                c->d_v[c->cur ^ 1], c->d_cpk, c->d_inv,
                                                                 c->geom(), c->w, c->a, kf);
             e = cudaGetLastError();
         }
@@ -287,7 +287,7 @@ void destroy_impl(hs_ctx* c) {
         if (c->stream) cudaStreamSynchronize(c->stream);
         cudaFree(c->d_prev); cudaFree(c->d_next);
         for (int i = 0; i < 2; ++i) { cudaFree(c->d_u[i]); cudaFree(c->d_v[i]); }
-        cudaFree(c->d_ixy); cudaFree(c->d_it); cudaFree(c->d_inv); cudaFree(c->d_out);
+        cudaFree(c->d_cpk); cudaFree(c->d_inv); cudaFree(c->d_out);
         for (auto& e : c->ev) if (e) cudaEventDestroy(e);
         if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
     }
@@ -383,8 +383,7 @@ int hs_create(const hs_config* cfg_in, hs_ctx** out) {
         HS_CREATE_CUDA(cudaMalloc(&c->d_u[i], npx * sizeof(float)));
         HS_CREATE_CUDA(cudaMalloc(&c->d_v[i], npx * sizeof(float)));
     }
-    HS_CREATE_CUDA(cudaMalloc(&c->d_ixy, npx * sizeof(__half2)));
-    HS_CREATE_CUDA(cudaMalloc(&c->d_it, npx * sizeof(__half)));
+    HS_CREATE_CUDA(cudaMalloc(&c->d_cpk, npx * sizeof(uint32_t)));
     HS_CREATE_CUDA(cudaMalloc(&c->d_inv, npx * sizeof(float)));
 
     // kernel selection: fused tile kernel for w in {2,3,4,5}, generic sweep otherwise
@@ -413,8 +412,7 @@ int hs_create(const hs_config* cfg_in, hs_ctx** out) {
             if ((rc = make_map(c, &c->tm_u[i], c->d_u[i], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, TS0::SX, TS0::SY))) return bail(rc);
             if ((rc = make_map(c, &c->tm_v[i], c->d_v[i], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, TS0::SX, TS0::SY))) return bail(rc);
         }
-        if ((rc = make_map(c, &c->tm_ixy, c->d_ixy, CU_TENSOR_MAP_DATA_TYPE_UINT32, 4, TS0::SX, TS0::SY))) return bail(rc);
-        if ((rc = make_map(c, &c->tm_it, c->d_it, CU_TENSOR_MAP_DATA_TYPE_UINT16, 2, TS0::SX, TS0::SY))) return bail(rc);
+        if ((rc = make_map(c, &c->tm_cpk, c->d_cpk, CU_TENSOR_MAP_DATA_TYPE_UINT32, 4, TS0::SX, TS0::SY))) return bail(rc);
         if ((rc = make_map(c, &c->tm_inv, c->d_inv, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, TS0::SX, TS0::SY))) return bail(rc);
     } else {
         c->k = 1;
@@ -519,10 +517,10 @@ int hs_gradients(hs_ctx* c, const uint8_t* prev, size_t ps, const uint8_t* next,
     char* o = static_cast<char*>(c->d_out);
     if (dt == HS_F64) {
         double* d = reinterpret_cast<double*>(o);
-        hs::k_unpack_grad<double><<<148 * 8, 256, 0, c->stream>>>(c->d_ixy, c->d_it, d, d + n, d + 2 * n, n);
+        hs::k_unpack_grad<double><<<148 * 8, 256, 0, c->stream>>>(c->d_cpk, d, d + n, d + 2 * n, n);
     } else {
         float* d = reinterpret_cast<float*>(o);
-        hs::k_unpack_grad<float><<<148 * 8, 256, 0, c->stream>>>(c->d_ixy, c->d_it, d, d + n, d + 2 * n, n);
+        hs::k_unpack_grad<float><<<148 * 8, 256, 0, c->stream>>>(c->d_cpk, d, d + n, d + 2 * n, n);
     }
     HS_CUDA(c, cudaGetLastError());
     c->timing.launches += 1;

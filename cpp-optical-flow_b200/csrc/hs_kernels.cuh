@@ -17,7 +17,6 @@
 #pragma once
 
 #include <cuda.h>
-#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -32,6 +31,17 @@ struct Geom {
     int oy0, oy1;   // rows this context produces: [oy0, oy1)
 };
 
+// Gradient coefficients are exact small integers (|Ix|,|Iy| <= 1020, |It| <= 255), so the three of
+// them share one 32-bit word: Ix in bits 31..21, Iy in 20..10, It in 9..0 (two's complement fields).
+__device__ __forceinline__ uint32_t pack_coef(int gx, int gy, int gt) {
+    return ((uint32_t)(gx & 0x7ff) << 21) | ((uint32_t)(gy & 0x7ff) << 10) | (uint32_t)(gt & 0x3ff);
+}
+__device__ __forceinline__ void unpack_coef(uint32_t w, float& ix, float& iy, float& it) {
+    ix = (float)((int)w >> 21);
+    iy = (float)((int)(w << 11) >> 21);
+    it = (float)((int)(w << 22) >> 22);
+}
+
 __device__ __forceinline__ int reflect101(int i, int n) {
     if (n == 1) return 0;
     if (i < 0) return -i;
@@ -41,8 +51,8 @@ __device__ __forceinline__ int reflect101(int i, int n) {
 
 // ------------------------------------------------------------------------------------------
 // K1: spatio-temporal gradients + per-pixel coefficients, one pass over the two uint8 frames.
-// Writes Ix,Iy as half2 (exact: |Ix|,|Iy| <= 1020 are integers), It as half (|It| <= 255) and
-// inv = 1/(alpha^2 + Ix^2 + Iy^2) as float.  4 pixels per thread, vector stores.
+// Writes {Ix,Iy,It} packed into one word per pixel (pack_coef) and inv = 1/(alpha^2+Ix^2+Iy^2)
+// as float: 8 B of coefficients per pixel.  4 pixels per thread, vector stores.
 // Frames: `frows` rows of `fpitch` bytes; buffer row y lives in frame row y + frow0 (frow0 = 1
 // when a seam row sits above).  BORDER_REFLECT_101 therefore only ever triggers at true image
 // borders.
@@ -50,8 +60,7 @@ __device__ __forceinline__ int reflect101(int i, int n) {
 __global__ void __launch_bounds__(256)
 k_grad_coeff(const uint8_t* __restrict__ prev, const uint8_t* __restrict__ next,
              size_t fpitch, size_t fimg, int frows, int frow0,
-             __half2* __restrict__ ixy, __half* __restrict__ itp, float* __restrict__ inv,
-             Geom g, float alpha2) {
+             uint32_t* __restrict__ cpk, float* __restrict__ inv, Geom g, float alpha2) {
     const int x0 = (blockIdx.x * 32 + threadIdx.x) * 4;
     const int y = blockIdx.y * 8 + threadIdx.y;
     const int b = blockIdx.z;
@@ -74,8 +83,7 @@ k_grad_coeff(const uint8_t* __restrict__ prev, const uint8_t* __restrict__ next,
         c[i] = r1[xr];
         d[i] = r2[xr];
     }
-    __half2 oxy[4];
-    __half ot[4];
+    uint32_t opk[4];
     float oinv[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
@@ -89,13 +97,11 @@ k_grad_coeff(const uint8_t* __restrict__ prev, const uint8_t* __restrict__ next,
             const float den = __fadd_rn(alpha2, (float)(gx * gx + gy * gy));               // :65-68
             iv = __fdiv_rn(1.0f, den);
         }
-        oxy[i] = __halves2half2(__int2half_rn(gx), __int2half_rn(gy));
-        ot[i] = __int2half_rn(gt);
+        opk[i] = pack_coef(gx, gy, gt);
         oinv[i] = iv;
     }
     const size_t o = (size_t)b * g.plane + (size_t)y * g.pitch + x0;
-    *reinterpret_cast<uint4*>(ixy + o) = *reinterpret_cast<uint4*>(oxy);
-    *reinterpret_cast<uint2*>(itp + o) = *reinterpret_cast<uint2*>(ot);
+    *reinterpret_cast<uint4*>(cpk + o) = make_uint4(opk[0], opk[1], opk[2], opk[3]);
     *reinterpret_cast<float4*>(inv + o) = make_float4(oinv[0], oinv[1], oinv[2], oinv[3]);
 }
 
@@ -119,8 +125,8 @@ __device__ __forceinline__ void hs_update(float su, float sv, float kf, float ix
 __global__ void __launch_bounds__(256)
 k_jacobi_generic(const float* __restrict__ u, const float* __restrict__ v,
                  float* __restrict__ un, float* __restrict__ vn,
-                 const __half2* __restrict__ ixy, const __half* __restrict__ itp,
-                 const float* __restrict__ inv, Geom g, int w, int a, float kf) {
+                 const uint32_t* __restrict__ cpk, const float* __restrict__ inv,
+                 Geom g, int w, int a, float kf) {
     const int x = blockIdx.x * 32 + threadIdx.x;
     const int y = g.oy0 + blockIdx.y * 8 + threadIdx.y;
     if (x >= g.W || y >= g.oy1) return;
@@ -145,9 +151,9 @@ k_jacobi_generic(const float* __restrict__ u, const float* __restrict__ v,
         sv = (dy == 0) ? hv : __fadd_rn(sv, hv);
     }
     const size_t o = base + (size_t)y * g.pitch + x;
-    const float2 xy = __half22float2(ixy[o]);
-    float nu, nv;
-    hs_update(su, sv, kf, xy.x, xy.y, __half2float(itp[o]), inv[o], nu, nv);
+    float ix, iy, it, nu, nv;
+    unpack_coef(cpk[o], ix, iy, it);
+    hs_update(su, sv, kf, ix, iy, it, inv[o], nu, nv);
     un[o] = nu;
     vn[o] = nv;
 }
@@ -204,7 +210,7 @@ __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
 // K3: k fused Jacobi sweeps per launch.
 //
 // One CTA owns a staged tile of SX x SY pixels (SX = 128 = 32 lanes x 4 px, SY = NWARP x R rows).
-// Five TMA boxes (u, v, IxIy, It, inv) land in shared memory; each thread then keeps its
+// Four TMA boxes (u, v, packed Ix/Iy/It, inv) land in shared memory; each thread then keeps its
 // 4 x R patch of u, v AND its coefficients in registers for all k sweeps.  Per sweep:
 //   1. row sums of the patch, horizontal neighbours by warp shuffle
 //   2. the patch's top/bottom row sums go to a double-buffered shared exchange array
@@ -222,17 +228,15 @@ struct TileShape {
     static constexpr int THREADS = NWARP * 32;
     static constexpr int EXROWS = SY + RL + RR;                       // exchange rows incl. zero pads
     static constexpr size_t BYTES_F32 = (size_t)SX * SY * 4;
-    static constexpr size_t BYTES_F16 = (size_t)SX * SY * 2;
     static constexpr size_t OFF_U = 0;
     static constexpr size_t OFF_V = OFF_U + BYTES_F32;
-    static constexpr size_t OFF_IXY = OFF_V + BYTES_F32;
-    static constexpr size_t OFF_INV = OFF_IXY + BYTES_F32;
-    static constexpr size_t OFF_IT = OFF_INV + BYTES_F32;
-    static constexpr size_t OFF_EX = OFF_IT + BYTES_F16;              // [2 buf][2 field][EXROWS][SX]
+    static constexpr size_t OFF_CPK = OFF_V + BYTES_F32;
+    static constexpr size_t OFF_INV = OFF_CPK + BYTES_F32;
+    static constexpr size_t OFF_EX = OFF_INV + BYTES_F32;             // [2 buf][2 field][EXROWS][SX]
     static constexpr size_t BYTES_EX = (size_t)2 * 2 * EXROWS * SX * 4;
     static constexpr size_t OFF_BAR = OFF_EX + BYTES_EX;
     static constexpr size_t SMEM = OFF_BAR + 16;
-    static constexpr uint32_t TX_BYTES = (uint32_t)(4 * BYTES_F32 + BYTES_F16);
+    static constexpr uint32_t TX_BYTES = (uint32_t)(4 * BYTES_F32);
 };
 
 // row sums of one patch row: 4 outputs from 4 own values + RL left + RR right neighbours
@@ -329,8 +333,7 @@ __device__ __forceinline__ void tile_sweeps(float (&u)[R][4], float (&v)[R][4],
 template <int RL, int RR, int R, int NWARP>
 __global__ void __launch_bounds__(NWARP * 32, 1)
 k_jacobi_tile(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CUtensorMap tm_v,
-              const __grid_constant__ CUtensorMap tm_ixy, const __grid_constant__ CUtensorMap tm_it,
-              const __grid_constant__ CUtensorMap tm_inv,
+              const __grid_constant__ CUtensorMap tm_cpk, const __grid_constant__ CUtensorMap tm_inv,
               float* __restrict__ un, float* __restrict__ vn, Geom g,
               int k, int hxl, int hyt, int vx, int vy, float kf) {
     using TS = TileShape<RL, RR, R, NWARP>;
@@ -339,9 +342,8 @@ k_jacobi_tile(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ 
     extern __shared__ __align__(128) unsigned char smem[];
     float* s_u = reinterpret_cast<float*>(smem + TS::OFF_U);
     float* s_v = reinterpret_cast<float*>(smem + TS::OFF_V);
-    __half2* s_ixy = reinterpret_cast<__half2*>(smem + TS::OFF_IXY);
+    uint32_t* s_cpk = reinterpret_cast<uint32_t*>(smem + TS::OFF_CPK);
     float* s_inv = reinterpret_cast<float*>(smem + TS::OFF_INV);
-    __half* s_it = reinterpret_cast<__half*>(smem + TS::OFF_IT);
     float* s_ex = reinterpret_cast<float*>(smem + TS::OFF_EX);
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem + TS::OFF_BAR);
 
@@ -355,20 +357,20 @@ k_jacobi_tile(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ 
     if (tid == 0) {
         tma_prefetch_desc(&tm_u);
         tma_prefetch_desc(&tm_v);
-        tma_prefetch_desc(&tm_ixy);
-        tma_prefetch_desc(&tm_it);
+        tma_prefetch_desc(&tm_cpk);
         tma_prefetch_desc(&tm_inv);
         mbar_init(bar, 1);
         fence_mbar_init();
     }
     __syncthreads();
+    // Start coordinates are multiples of 4 floats = 16 B: UTMALDG faults ("illegal instruction")
+    // on sm_100a when the innermost start offset is not 16-byte aligned (measured, tools/tma_probe.cu).
     if (tid == 0) {
         mbar_expect_tx(bar, TS::TX_BYTES);
         tma_load_3d(s_u, &tm_u, bar, tx0, ty0, b);
         tma_load_3d(s_v, &tm_v, bar, tx0, ty0, b);
-        tma_load_3d(s_ixy, &tm_ixy, bar, tx0, ty0, b);
+        tma_load_3d(s_cpk, &tm_cpk, bar, tx0, ty0, b);
         tma_load_3d(s_inv, &tm_inv, bar, tx0, ty0, b);
-        tma_load_3d(s_it, &tm_it, bar, tx0, ty0, b);
     }
     // while the boxes are in flight: zero the exchange pad rows (above row 0 / below row SY-1)
     for (int i = tid; i < 2 * 2 * (RL + RR) * TS::SX; i += TS::THREADS) {
@@ -402,21 +404,14 @@ k_jacobi_tile(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ 
         const float4 qu = *reinterpret_cast<const float4*>(s_u + so);
         const float4 qv = *reinterpret_cast<const float4*>(s_v + so);
         const float4 qi = *reinterpret_cast<const float4*>(s_inv + so);
-        const uint4 qxy = *reinterpret_cast<const uint4*>(s_ixy + so);
-        const uint2 qt = *reinterpret_cast<const uint2*>(s_it + so);
+        const uint4 qc = *reinterpret_cast<const uint4*>(s_cpk + so);
         u[j][0] = qu.x; u[j][1] = qu.y; u[j][2] = qu.z; u[j][3] = qu.w;
         v[j][0] = qv.x; v[j][1] = qv.y; v[j][2] = qv.z; v[j][3] = qv.w;
         iv[j][0] = qi.x; iv[j][1] = qi.y; iv[j][2] = qi.z; iv[j][3] = qi.w;
-        const uint32_t wxy[4] = {qxy.x, qxy.y, qxy.z, qxy.w};
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-            const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&wxy[c]));
-            ix[j][c] = f.x;
-            iy[j][c] = f.y;
-        }
-        const float2 t01 = __half22float2(*reinterpret_cast<const __half2*>(&qt.x));
-        const float2 t23 = __half22float2(*reinterpret_cast<const __half2*>(&qt.y));
-        it[j][0] = t01.x; it[j][1] = t01.y; it[j][2] = t23.x; it[j][3] = t23.y;
+        unpack_coef(qc.x, ix[j][0], iy[j][0], it[j][0]);
+        unpack_coef(qc.y, ix[j][1], iy[j][1], it[j][1]);
+        unpack_coef(qc.z, ix[j][2], iy[j][2], it[j][2]);
+        unpack_coef(qc.w, ix[j][3], iy[j][3], it[j][3]);
     }
     __syncthreads();  // exchange pad rows are zeroed before anyone reads them
 
@@ -460,15 +455,16 @@ k_widen(const float* __restrict__ a, const float* __restrict__ b2, double* __res
 
 template <typename T>
 __global__ void __launch_bounds__(256)
-k_unpack_grad(const __half2* __restrict__ ixy, const __half* __restrict__ itp, T* __restrict__ gx,
-              T* __restrict__ gy, T* __restrict__ gt, long long n) {
+k_unpack_grad(const uint32_t* __restrict__ cpk, T* __restrict__ gx, T* __restrict__ gy,
+              T* __restrict__ gt, long long n) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long stride = (long long)gridDim.x * blockDim.x;
     for (long long p = i; p < n; p += stride) {
-        const float2 f = __half22float2(ixy[p]);
-        gx[p] = (T)f.x;
-        gy[p] = (T)f.y;
-        gt[p] = (T)__half2float(itp[p]);
+        float ix, iy, it;
+        unpack_coef(cpk[p], ix, iy, it);
+        gx[p] = (T)ix;
+        gy[p] = (T)iy;
+        gt[p] = (T)it;
     }
 }
 
