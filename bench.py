@@ -1,0 +1,327 @@
+#!/usr/bin/env python
+"""bench.py - Horn-Schunck Mpixel-iterations/s on B200 (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+                    [--workload 1080p|4k|kitti|slab16k] [--window 3|5] [--iters T] [--k K]
+
+A *step* is one complete solve of the workload: gradient/coefficient stage + T Jacobi sweeps.
+  value  : whole-job Mpixel-iterations/s with the frames already resident in HBM
+           (CUDA events on the launching stream, max over ranks)
+  e2e    : the same metric through the reference-facing call hs_solve() with HOST buffers:
+           H2D of both uint8 frames and D2H of u, v as float64 (the reference's CV_64FC1) inside
+           the timed region
+  roofline: the fused Jacobi kernel against the measured HBM peak, 32 algorithmic bytes per
+           pixel-iteration (SURVEY.md 8d / DESIGN.md), duration from CUDA events around the sweeps
+  cpu_baseline / --impl reference: the reference's CPU path (oracle/hs_oracle.py::cv_flow, the
+           line-by-line cv2 restatement of hornSchunck.cpp - C++ OpenCV is not in this image, so
+           hornSchunck.cpp itself cannot be compiled) on a bounded sample of the same workload.
+N > 1 (torchrun, one rank per GPU): the default workloads give every rank its own frame pair
+(BASELINE config 4: independent pairs, no communication, weak scaling); `slab16k` is the
+row-slab decomposition of one 16384^2 pair with halo exchange (config 5, strong scaling).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (height, width, default iterations, BASELINE.json config it restates)
+    "1080p": (1080, 1920, 1000, "configs[1]: synthetic textured 1920x1080 pair, alpha=1, 1000 Jacobi iterations"),
+    "4k": (2160, 3840, 2000, "configs[2]: synthetic 3840x2160 pair, 2000 iterations"),
+    "kitti": (375, 1242, 100, "configs[0]: bundled 1242x375 pair size, w=5, 100 iterations (synthetic texture)"),
+    "slab16k": (16384, 16384, 5000, "configs[4]: one 16384x16384 pair, 5000 iterations, row slabs + halo exchange"),
+}
+ALGO_BYTES_PER_PIXEL_ITER = 32.0       # u,v read 8 + Ix,Iy,It,inv read 16 + u,v write 8 (fp32)
+METRIC = "HS Mpixel-iter/s"
+
+
+def dist_env():
+    return int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+
+
+def measured_hbm_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.rows, self.proc, self.index = [], None, index
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def __exit__(self, *exc):
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+            except Exception:
+                continue
+            for n, val in zip(names, r[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(n)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------
+# reference arm / cpu_baseline: the reference's own CPU algorithm on the box's host cores
+# ---------------------------------------------------------------------------------------------
+def cpu_reference_rate(prev, nxt, window, alpha, seconds_budget):
+    """Time the cv2 restatement of hornSchunck.cpp on a bounded number of sweeps of this workload."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import cv2
+    import hs_oracle
+    threads = cv2.getNumThreads()
+    t0 = time.perf_counter()
+    hs_oracle.cv_flow(prev, nxt, window, 2, alpha)          # includes the gradient stage, like a solve
+    per_iter = max((time.perf_counter() - t0) / 2.0, 1e-4)
+    iters = int(min(max(seconds_budget / per_iter, 4), 400))
+    t0 = time.perf_counter()
+    hs_oracle.cv_flow(prev, nxt, window, iters, alpha)
+    dt = time.perf_counter() - t0
+    rate = prev.shape[0] * prev.shape[1] * iters / dt / 1e6
+    return rate, threads, iters, dt, cv2.__version__
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    from cpp_optical_flow_b200 import synth
+    H, W, T_default, cfgname = WORKLOADS[args.workload]
+    if args.workload == "slab16k":       # bounded sample: a 16384 x 512 strip of the 16K^2 frame
+        H = 512
+    prev, nxt = synth.frame_pair(H, W)
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import cv2
+    import hs_oracle
+    iters = args.ref_iters
+    for _ in range(args.warmup):
+        hs_oracle.cv_flow(prev, nxt, args.window, max(1, iters // 4), 1.0)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        hs_oracle.cv_flow(prev, nxt, args.window, iters, 1.0)
+    dt = time.perf_counter() - t0
+    val = H * W * iters * args.steps / dt / 1e6
+    sample = f"{W}x{H} frame pair, {iters} of {args.iters or T_default} sweeps per step (throughput is per sweep)"
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "Mpixel-iter/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"{args.workload}: {cfgname}", "window": args.window, "alpha": 1.0,
+                       "iterations": args.iters or T_default},
+            "cpu_baseline": {"value": val, "unit": "Mpixel-iter/s", "cores": cv2.getNumThreads(), "kind": "port",
+                             "sample": sample,
+                             "what": "oracle/hs_oracle.py::cv_flow = hornSchunck.cpp:19-75 through cv2 "
+                                     f"{cv2.__version__} (C++ OpenCV absent: hornSchunck.cpp not compilable here)"},
+            "e2e": {"value": val, "unit": "Mpixel-iter/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------
+# our arm
+# ---------------------------------------------------------------------------------------------
+def run_ours(args, rank, local_rank, world):
+    import torch
+    import torch.distributed as dist
+    import cpp_optical_flow_b200 as pkg
+    from cpp_optical_flow_b200 import hs_ctypes as HC, synth
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device - the product path has no CPU fallback "
+                         "(use --impl reference for the CPU reference arm)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    if args.workload == "slab16k":
+        from cpp_optical_flow_b200 import slab
+        return slab.bench_slab(args, rank, local_rank, world, METRIC, ALGO_BYTES_PER_PIXEL_ITER, measured_hbm_peak)
+
+    H, W, T_default, cfgname = WORKLOADS[args.workload]
+    T = args.iters or T_default
+    window = args.window
+    dev = torch.device("cuda", local_rank)
+    stream = torch.cuda.Stream(device=dev)
+    prev, nxt = synth.video_pair(rank, H, W) if world > 1 else synth.frame_pair(H, W)
+
+    solver = pkg.Solver(W, H, window, T, 1.0, device=local_rank, temporal_k=args.k, stream=stream.cuda_stream)
+    solver.upload(prev, nxt)
+    solver.sync()
+    flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)      # > 126 MB L2
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+
+    with torch.cuda.stream(stream):
+        for _ in range(args.warmup):
+            solver.solve_device(); solver.sync()
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+        iter_ms, prep_ms, launches = [], [], 0
+        barrier(); torch.cuda.synchronize()
+        with ClockSampler(local_rank) as clocks:
+            wall0 = time.perf_counter()
+            for s, e in ev:
+                flush.zero_()                      # cold L2 at the start of every step
+                s.record(stream)
+                solver.solve_device()
+                e.record(stream)
+                solver.sync()
+                t = solver.timing()
+                iter_ms.append(t.iterate_ms); prep_ms.append(t.prepare_ms); launches += t.launches
+            torch.cuda.synchronize(); barrier()
+            wall = time.perf_counter() - wall0
+        step_ms = [s.elapsed_time(e) for s, e in ev]
+    tm = solver.timing()
+    total_ms = torch.tensor([sum(step_ms)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
+    total_s = float(total_ms.item()) / 1e3
+    work = float(H) * W * T * args.steps * world            # pixel-iterations, all ranks
+    value = work / total_s / 1e6
+
+    # ---- end to end through hs_solve with pinned host buffers -------------------------------
+    hp = torch.from_numpy(prev).pin_memory(); hn = torch.from_numpy(nxt).pin_memory()
+    hu = torch.empty((H, W), dtype=torch.float64).pin_memory(); hv = torch.empty((H, W), dtype=torch.float64).pin_memory()
+    lib = HC.load_library()
+
+    def solve_host():
+        rc = lib.hs_solve(solver._ctx, hp.data_ptr(), W, 0, hn.data_ptr(), W, 0, hu.data_ptr(), W * 8, 0,
+                          hv.data_ptr(), W * 8, 0, HC.HS_F64)
+        if rc:
+            raise RuntimeError(lib.hs_last_error(solver._ctx))
+
+    e2e_steps = max(3, min(args.steps, 10))
+    solve_host()
+    barrier(); torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        with torch.cuda.stream(stream):
+            flush.zero_()
+        stream.synchronize()
+        solve_host()
+    torch.cuda.synchronize()
+    e2e_t = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
+    e2e_value = float(H) * W * T * e2e_steps * world / float(e2e_t.item()) / 1e6
+    et = solver.timing()
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel (the Jacobi sweeps) -----------------------------------
+    peak, peak_src = measured_hbm_peak()
+    it_s = float(np.mean(iter_ms)) / 1e3
+    achieved = ALGO_BYTES_PER_PIXEL_ITER * H * W * T / it_s / 1e9
+    sweep_launches = launches // args.steps - 1              # minus the gradient kernel
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(f"{args.workload}_w{window}")
+    except Exception:
+        pass
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": traffic, "peak_source": peak_src,
+                "kernel": "k_jacobi_tile" if tm.kernel_id == 1 else "k_jacobi_generic",
+                "launches_per_step": sweep_launches, "avg_launch_us": it_s / max(sweep_launches, 1) * 1e6,
+                "algorithmic_bytes_per_launch": ALGO_BYTES_PER_PIXEL_ITER * H * W * T / max(sweep_launches, 1),
+                "fused_sweeps_per_launch": tm.temporal_k,
+                "note": "32 B per pixel-iteration, no credit for temporal blocking: k fused sweeps per HBM round "
+                        "trip is why frac can exceed 1"}
+
+    cpu = None
+    if world == 1 and not args.no_cpu:
+        rate, threads, its, dt, cvv = cpu_reference_rate(prev, nxt, window, 1.0, args.cpu_seconds)
+        cpu = {"value": rate, "unit": "Mpixel-iter/s", "cores": threads, "kind": "port",
+               "sample": f"same {W}x{H} pair, {its} of {T} sweeps ({dt:.1f} s), cv2 {cvv} restatement of hornSchunck.cpp"}
+
+    line = {"metric": METRIC, "value": value, "unit": "Mpixel-iter/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": float(np.mean(step_ms)), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"{args.workload}: {cfgname}", "window": window, "alpha": 1.0, "iterations": T,
+                       "pairs_per_rank_per_step": 1, "parallelism": f"independent pairs x{world}" if world > 1 else "1 gpu",
+                       "l2": "512 MiB memset before every step (cold L2 at step start; events exclude it)",
+                       "temporal_k": tm.temporal_k},
+            "roofline": roofline,
+            "e2e": {"value": e2e_value, "unit": "Mpixel-iter/s", "h2d_bytes_per_step": 2 * H * W,
+                    "d2h_bytes_per_step": 2 * H * W * 8, "steps": e2e_steps,
+                    "last_step_ms": {"h2d": et.h2d_ms, "prepare": et.prepare_ms, "iterate": et.iterate_ms,
+                                     "d2h": et.d2h_ms, "total": et.total_ms}},
+            "gpu_launches": launches, "clocks": clocks.summary(),
+            "wall_ms_per_step_incl_flush": wall / args.steps * 1e3,
+            "prepare_ms": float(np.mean(prep_ms)), "iterate_ms": float(np.mean(iter_ms))}
+    if cpu:
+        line["cpu_baseline"] = cpu
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="1080p", choices=sorted(WORKLOADS))
+    ap.add_argument("--window", type=int, default=3, help="windowSize (3 = the north star's 3x3; main.cpp uses 5)")
+    ap.add_argument("--iters", type=int, default=0, help="override the workload's iteration count")
+    ap.add_argument("--k", type=int, default=0, help="fused sweeps per launch (0 = library default)")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline sample")
+    ap.add_argument("--ref-iters", type=int, default=16, help="--impl reference: sweeps per step (bounded sample)")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    rank, local_rank, world = dist_env()
+    if args.impl == "reference":
+        return run_reference(args, rank, world)
+    if world != args.gpus and rank == 0:
+        print(f"bench.py: --gpus {args.gpus} but WORLD_SIZE={world}; launch with torchrun for N>1", file=sys.stderr)
+    run_ours(args, rank, local_rank, world)
+
+
+if __name__ == "__main__":
+    main()

@@ -69,7 +69,7 @@ struct hs_ctx {
 
     cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     hs_timing timing{};
-    bool uploaded = false, prepared = false;
+    bool uploaded = false, prepared = false, timing_pending = false;
     std::string err;
 
     hs::Geom geom() const {
@@ -454,9 +454,14 @@ int hs_solve_device(hs_ctx* c) {
     if (!c) return HS_ERR_INVALID_ARG;
     DevGuard g(c->dev);
     c->timing.launches = 0;
+    HS_CUDA(c, cudaEventRecord(c->ev[1], c->stream));
     int rc = do_prepare(c);
     if (rc) return rc;
-    return do_iterate(c, c->T);
+    HS_CUDA(c, cudaEventRecord(c->ev[2], c->stream));
+    if ((rc = do_iterate(c, c->T))) return rc;
+    HS_CUDA(c, cudaEventRecord(c->ev[3], c->stream));
+    c->timing_pending = true;   // resolved by the next hs_sync
+    return HS_OK;
 }
 
 int hs_download(hs_ctx* c, void* u, size_t us, size_t uis, void* v, size_t vs, size_t vis, int dt) {
@@ -472,6 +477,13 @@ int hs_sync(hs_ctx* c) {
     if (!c) return HS_ERR_INVALID_ARG;
     DevGuard g(c->dev);
     HS_CUDA(c, cudaStreamSynchronize(c->stream));
+    if (c->timing_pending) {
+        c->timing_pending = false;
+        c->timing.h2d_ms = c->timing.d2h_ms = 0.f;
+        c->timing.prepare_ms = ev_ms(c->ev[1], c->ev[2]);
+        c->timing.iterate_ms = ev_ms(c->ev[2], c->ev[3]);
+        c->timing.total_ms = ev_ms(c->ev[1], c->ev[3]);
+    }
     return HS_OK;
 }
 

@@ -1,0 +1,285 @@
+"""Row-slab decomposition of one large frame pair over several GPUs (BASELINE config 5).
+
+One process per GPU (torch.distributed over NCCL/NVLink).  Rank r owns a contiguous band of
+rows; per fused launch of k sweeps its kernel reads a*k rows above and (w/2)*k rows below the
+band (a = anchor = w - w/2 - 1, hornSchunck.cpp:54), so after every launch each seam exchanges
+exactly those rows of u and of v with its two neighbours - rows are contiguous in the pitched
+planes, so a halo is one contiguous send, no packing kernel.  Coefficients are never exchanged:
+every rank gets the frame rows of its band + halo (+1 seam row for the Sobel taps) and recomputes
+them.  The result is bit-identical to the single-GPU solve (Jacobi has no ordering freedom).
+
+The exchange logic is written against torch tensors only, so the same code runs on CPU tensors
+with the gloo backend in tests/test_slab_gloo.py.
+"""
+from __future__ import annotations
+
+import json
+import os
+import time
+from dataclasses import dataclass
+
+import numpy as np
+
+
+def radii(window: int):
+    """(taps above/left, taps below/right) of the box window: anchor a and w-1-a."""
+    a = window - window // 2 - 1
+    return a, window - 1 - a
+
+
+def partition_rows(height: int, world: int):
+    """Balanced contiguous row bands; the first (height % world) bands get one extra row."""
+    base, extra = divmod(height, world)
+    bounds, y = [], 0
+    for r in range(world):
+        n = base + (1 if r < extra else 0)
+        bounds.append((y, y + n))
+        y += n
+    return bounds
+
+
+@dataclass
+class SlabGeometry:
+    rank: int
+    world: int
+    height: int          # full image
+    width: int
+    window: int
+    k: int               # sweeps fused per launch == sweeps between halo exchanges
+    y0: int              # owned rows [y0, y1) in image coordinates
+    y1: int
+    b0: int              # buffer rows [b0, b1) = owned rows + halos, clipped to the image
+    b1: int
+    f0: int              # frame rows [f0, f1) = buffer rows + one Sobel row at each seam
+    f1: int
+    top_seam: bool
+    bottom_seam: bool
+
+    @property
+    def halo_top(self):
+        return self.y0 - self.b0
+
+    @property
+    def halo_bottom(self):
+        return self.b1 - self.y1
+
+    @property
+    def out_rows(self):
+        """Owned rows in buffer-local coordinates."""
+        return (self.y0 - self.b0, self.y1 - self.b0)
+
+    @property
+    def rows(self):
+        return self.b1 - self.b0
+
+
+def plan(height: int, width: int, world: int, rank: int, window: int, k: int) -> SlabGeometry:
+    rl, rr = radii(window)
+    bounds = partition_rows(height, world)
+    y0, y1 = bounds[rank]
+    need = max(rl, rr) * k
+    if world > 1 and min(b - a for a, b in bounds) < need:
+        raise ValueError(f"row slabs of {min(b - a for a, b in bounds)} rows are thinner than the {need}-row halo "
+                         f"(window {window}, k {k}); use fewer ranks or a smaller k")
+    b0 = max(0, y0 - rl * k) if rank > 0 else y0
+    b1 = min(height, y1 + rr * k) if rank < world - 1 else y1
+    top_seam, bottom_seam = b0 > 0, b1 < height
+    return SlabGeometry(rank, world, height, width, window, k, y0, y1, b0, b1,
+                        b0 - (1 if top_seam else 0), b1 + (1 if bottom_seam else 0), top_seam, bottom_seam)
+
+
+def exchange_halos(geom: SlabGeometry, planes, group=None):
+    """Refresh the halo rows of `planes` (2-D torch tensors [buffer rows, pitch], the CURRENT u and
+    v of this rank) from the neighbours' owned rows.  Neighbour-only send/recv, one batch."""
+    import torch.distributed as dist
+    rl, rr = radii(geom.window)
+    up, dn = rl * geom.k, rr * geom.k         # rows this rank needs from above / from below
+    o0, o1 = geom.out_rows
+    ops = []
+    for t in planes:
+        if geom.rank > 0:                     # seam above: my top halo <- neighbour's last rows
+            if dn:
+                ops.append(dist.P2POp(dist.isend, t[o0:o0 + dn], geom.rank - 1, group))
+            if up:
+                ops.append(dist.P2POp(dist.irecv, t[o0 - up:o0], geom.rank - 1, group))
+        if geom.rank < geom.world - 1:        # seam below
+            if up:
+                ops.append(dist.P2POp(dist.isend, t[o1 - up:o1], geom.rank + 1, group))
+            if dn:
+                ops.append(dist.P2POp(dist.irecv, t[o1:o1 + dn], geom.rank + 1, group))
+    if not ops:
+        return
+    for req in dist.batch_isend_irecv(ops):
+        req.wait()
+
+
+class _DevMem:
+    """Expose a raw device pointer to torch through __cuda_array_interface__ (no copy)."""
+
+    def __init__(self, ptr, shape, typestr="<f4"):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (int(ptr), False),
+                                         "version": 3, "strides": None}
+
+
+class DeviceSlab:
+    """One rank's slab on its GPU: an hs_ctx sized for band + halo, plus torch views of u, v."""
+
+    def __init__(self, geom: SlabGeometry, iterations: int, alpha: float, device: int, stream=None):
+        import torch
+        from . import hs_ctypes as H
+        from .horn_schunck import Solver
+        self.geom, self.iterations = geom, iterations
+        flags = (H.FLAG_TOP_IS_SEAM if geom.top_seam else 0) | (H.FLAG_BOTTOM_IS_SEAM if geom.bottom_seam else 0)
+        self.solver = Solver(geom.width, geom.rows, geom.window, iterations, alpha, device=device,
+                             temporal_k=geom.k, flags=flags, out_rows=geom.out_rows, stream=stream)
+        self.k = self.solver.timing().temporal_k
+        if self.k != geom.k:
+            raise ValueError(f"library chose k={self.k}, slab plan was made for k={geom.k}")
+        self._torch = torch
+        self._device = torch.device("cuda", device)
+        self._views = {}
+
+    def close(self):
+        self.solver.close()
+
+    def upload(self, prev_rows, next_rows):
+        """prev_rows/next_rows: uint8 [f1 - f0, width] = frame rows geom.f0 .. geom.f1 of the image."""
+        self.solver.upload(prev_rows, next_rows)
+
+    def planes(self):
+        """torch views [rows, pitch] of the current u and v (they ping-pong between two buffers)."""
+        dv = self.solver.device_view()
+        out = []
+        for ptr in (dv.u, dv.v):
+            if ptr not in self._views:
+                pitch = dv.flow_pitch // 4
+                self._views[ptr] = self._torch.as_tensor(_DevMem(ptr, (dv.height, pitch)), device=self._device)
+            out.append(self._views[ptr])
+        return out
+
+    def run(self, exchange=exchange_halos, group=None):
+        """prepare + `iterations` sweeps, exchanging halos after every fused launch but the last."""
+        self.solver.prepare()
+        left = self.iterations
+        launches = 0
+        while left > 0:
+            kk = min(self.k, left)
+            self.solver.iterate(kk)
+            left -= kk
+            launches += 1
+            if left > 0 and self.geom.world > 1:
+                exchange(self.geom, self.planes(), group)
+        return launches
+
+    def download(self, dtype=np.float32):
+        return self.solver.download(dtype)
+
+
+def solve_slabs_single_process(prev, nxt, window, iterations, alpha, nslab, temporal_k=0, device=0):
+    """N slab contexts on ONE GPU, halos copied device-to-device by the host between launches.
+    Exercises exactly the kernels / row ranges / seam handling of the multi-GPU path (used by the
+    GPU tests; never run waiting kernels of several ranks concurrently on one GPU)."""
+    import torch
+    from .horn_schunck import Solver
+    H, W = prev.shape
+    probe = Solver(W, max(H // nslab, 1), window, iterations, alpha, device=device, temporal_k=temporal_k)
+    k = probe.timing().temporal_k
+    probe.close()
+    geoms = [plan(H, W, nslab, r, window, k) for r in range(nslab)]
+    slabs = [DeviceSlab(g, iterations, alpha, device) for g in geoms]
+    rl, rr = radii(window)
+    up, dn = rl * k, rr * k
+    try:
+        for s in slabs:
+            g = s.geom
+            s.upload(prev[g.f0:g.f1], nxt[g.f0:g.f1])
+            s.solver.prepare()
+        left = iterations
+        while left > 0:
+            kk = min(k, left)
+            for s in slabs:
+                s.solver.iterate(kk)
+            left -= kk
+            if left > 0:
+                for s in slabs:
+                    s.solver.sync()
+                views = [s.planes() for s in slabs]
+                for r in range(nslab - 1):               # seam between slab r (above) and r + 1 (below)
+                    (a0, a1), (c0, c1) = geoms[r].out_rows, geoms[r + 1].out_rows
+                    for f in range(2):
+                        if up:
+                            views[r + 1][f][c0 - up:c0].copy_(views[r][f][a1 - up:a1])
+                        if dn:
+                            views[r][f][a1:a1 + dn].copy_(views[r + 1][f][c0:c0 + dn])
+                torch.cuda.synchronize()
+        parts = [s.download(np.float32) for s in slabs]
+    finally:
+        for s in slabs:
+            s.close()
+    return np.concatenate([p[0] for p in parts]), np.concatenate([p[1] for p in parts])
+
+
+def bench_slab(args, rank, local_rank, world, metric, algo_bytes, peak_fn):
+    """bench.py --workload slab16k: one 16384^2 pair, row slabs, halo exchange every k sweeps.
+    Strong scaling: total work is fixed, value = pixel-iterations of the whole image / max time."""
+    import torch
+    import torch.distributed as dist
+    from . import synth
+    H = W = int(os.environ.get("HS_SLAB_SIZE", 16384))
+    T = args.iters or 5000
+    window = args.window
+    rl, rr = radii(window)
+    k = args.k or max(1, 4 // max(1, max(rl, rr)))
+    geom = plan(H, W, world, rank, window, k)
+    dev = torch.device("cuda", local_rank)
+    prev, nxt = synth.frame_pair(geom.f1 - geom.f0, W, y0=geom.f0)
+    slab = DeviceSlab(geom, T, 1.0, local_rank, stream=torch.cuda.current_stream().cuda_stream)
+    slab.upload(prev, nxt)
+    slab.solver.sync()
+    flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+
+    warm_T = min(T, 8 * k)
+    slab.iterations = warm_T
+    for _ in range(args.warmup):
+        slab.run(); torch.cuda.synchronize()
+    slab.iterations = T
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    launches = 0
+    barrier(); torch.cuda.synchronize()
+    wall0 = time.perf_counter()
+    for s, e in ev:
+        flush.zero_()
+        barrier()
+        s.record()
+        launches += slab.run() + 1
+        e.record()
+        torch.cuda.synchronize()
+    barrier()
+    wall = time.perf_counter() - wall0
+    total = torch.tensor([sum(s.elapsed_time(e) for s, e in ev)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(total, op=dist.ReduceOp.MAX)
+    total_s = float(total.item()) / 1e3
+    value = float(H) * W * T * args.steps / total_s / 1e6
+    if rank == 0:
+        peak, src = peak_fn()
+        achieved = algo_bytes * H * W * T * args.steps / total_s / 1e9 / world     # per GPU
+        line = {"metric": metric, "value": value, "unit": "Mpixel-iter/s", "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": total_s / args.steps * 1e3, "higher_is_better": True,
+                "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": f"slab16k: one {W}x{H} pair, {T} sweeps, row slabs", "window": window,
+                           "alpha": 1.0, "iterations": T, "temporal_k": k,
+                           "parallelism": f"{world} row slabs, {rl * k}+{rr * k} halo rows per seam every {k} sweeps",
+                           "l2": "inputs (GBs per GPU) exceed L2; 512 MiB memset before every step anyway"},
+                "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                             "frac": achieved / peak, "traffic": None, "peak_source": src,
+                             "note": "per GPU, includes halo exchange time"},
+                "e2e": None, "gpu_launches": launches, "wall_ms_per_step": wall / args.steps * 1e3}
+        print(json.dumps(line), flush=True)
+    slab.close()
+    if world > 1:
+        dist.destroy_process_group()

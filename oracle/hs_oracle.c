@@ -56,33 +56,37 @@ static inline int reflect101(int i, int n) {
         }                                                                                          \
     }                                                                                              \
                                                                                                    \
-    /* one filter2D(BORDER_CONSTANT) pass, :60-61 */                                               \
-    static void box_##SUF(const REAL* f, REAL* out, int H, int W, int w) {                         \
+    /* one filter2D(BORDER_CONSTANT) pass, :60-61.  `pad` is a zeroed (H+w-1) x (W+w-1) scratch  */    \
+    /* plane: the image is copied to its centre, so out-of-image taps read 0 (= BORDER_CONSTANT)   */    \
+    /* and every pixel still accumulates kf*tap in dy-major / dx-minor order.                      */    \
+    static void box_##SUF(const REAL* restrict f, REAL* restrict out, REAL* restrict pad, int H, int W, int w) {              \
         const int a = w - w / 2 - 1;                                             /* :54 */         \
         const REAL kf = (REAL)1 / (REAL)(w * w);                                 /* :53 */         \
+        const size_t PW = (size_t)W + w - 1;                                                       \
         _Pragma("omp parallel for schedule(static)")                                               \
         for (int y = 0; y < H; ++y)                                                                \
-            for (int x = 0; x < W; ++x) {                                                          \
-                REAL acc = 0;                                                                      \
-                for (int dy = 0; dy < w; ++dy) {                                                   \
-                    int yy = y + dy - a;                                                           \
-                    for (int dx = 0; dx < w; ++dx) {                                               \
-                        int xx = x + dx - a;                                                       \
-                        REAL t = (yy >= 0 && yy < H && xx >= 0 && xx < W)                          \
-                                     ? f[(size_t)yy * W + xx] : (REAL)0;                           \
-                        acc += kf * t;                                                             \
-                    }                                                                              \
-                }                                                                                  \
-                out[(size_t)y * W + x] = acc;                                                      \
+            memcpy(pad + (size_t)(y + a) * PW + a, f + (size_t)y * W, (size_t)W * sizeof(REAL));   \
+        _Pragma("omp parallel for schedule(static)")                                               \
+        for (int y = 0; y < H; ++y) {                                                              \
+            REAL* restrict o = out + (size_t)y * W;                                                    \
+            for (int x = 0; x < W; ++x) o[x] = 0;                                                  \
+            for (int dy = 0; dy < w; ++dy) {                                                       \
+                const REAL* restrict r = pad + (size_t)(y + dy) * PW;                                    \
+                for (int dx = 0; dx < w; ++dx)                                                     \
+                    for (int x = 0; x < W; ++x) o[x] += kf * r[x + dx];                            \
             }                                                                                      \
+        }                                                                                          \
     }                                                                                              \
                                                                                                    \
     /* hornSchunck.cpp:43-75.  u, v: H*W outputs.  Returns 0, or -1 if out of memory. */           \
     int hs_oracle_flow_##SUF(const uint8_t* prev, const uint8_t* next, int H, int W, int w,        \
                              int iters, double alpha, REAL* u, REAL* v) {                          \
         size_t n = (size_t)H * W;                                                                  \
-        REAL* buf = (REAL*)malloc(n * 6 * sizeof(REAL));                                           \
+        size_t np_ = ((size_t)H + w - 1) * ((size_t)W + w - 1);                                    \
+        REAL* buf = (REAL*)malloc((n * 6 + np_) * sizeof(REAL));                                   \
         if (!buf) return -1;                                                                       \
+        REAL* pad = buf + 6 * n;                                                                   \
+        memset(pad, 0, np_ * sizeof(REAL));                                                        \
         REAL *gx = buf, *gy = buf + n, *gt = buf + 2 * n, *den = buf + 3 * n;                      \
         REAL *ua = buf + 4 * n, *va = buf + 5 * n;                                                 \
         hs_oracle_gradients_##SUF(prev, next, H, W, gx, gy, gt);                 /* :46 */         \
@@ -91,8 +95,8 @@ static inline int reflect101(int i, int n) {
         const REAL a2 = (REAL)alpha * (REAL)alpha;                                                 \
         for (size_t i = 0; i < n; ++i) den[i] = a2 + gx[i] * gx[i] + gy[i] * gy[i];                \
         for (int it = 0; it < iters; ++it) {                                     /* :56 */         \
-            box_##SUF(u, ua, H, W, w);                                           /* :60 */         \
-            box_##SUF(v, va, H, W, w);                                           /* :61 */         \
+            box_##SUF(u, ua, pad, H, W, w);                                          /* :60 */         \
+            box_##SUF(v, va, pad, H, W, w);                                          /* :61 */         \
             _Pragma("omp parallel for schedule(static)")                                           \
             for (size_t i = 0; i < n; ++i) {                                                       \
                 REAL c = (gx[i] * ua[i] + gy[i] * va[i] + gt[i]) / den[i];       /* :63-68 */      \

@@ -47,8 +47,7 @@ def c_oracle():
             h, wd = prev.shape
             u = np.zeros((h, wd), dtype)
             v = np.zeros((h, wd), dtype)
-            if threads:
-                lib.hs_oracle_set_threads(int(threads))
+            lib.hs_oracle_set_threads(int(threads) if threads else 1)   # 1 thread: vCPUs here do not scale
             fn = lib.hs_oracle_flow_f64 if np.dtype(dtype) == np.float64 else lib.hs_oracle_flow_f32
             vp = ctypes.c_void_p
             rc = fn(vp(prev.ctypes.data), vp(nxt.ctypes.data), h, wd, int(w), int(iters),

@@ -1,0 +1,108 @@
+"""CPU checks of the drop-in boundary: libhs_b200.so builds for sm_100a, loads without a GPU,
+exports every symbol include/hs.h declares, validates arguments, and refuses to run on the CPU."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, has_gpu
+
+
+def declared_functions():
+    text = open(os.path.join(ROOT, "include", "hs.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(hs_[a-z_0-9]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol(pkg):
+    from cpp_optical_flow_b200 import hs_ctypes as H
+    lib = pkg.load_library()
+    names = declared_functions()
+    assert set(names) == set(H.SYMBOLS), (names, H.SYMBOLS)
+    for n in names:
+        assert getattr(lib, n) is not None
+    assert lib.hs_version() == 100
+
+
+def test_library_is_built_for_sm_100a_only(pkg):
+    from cpp_optical_flow_b200 import _build
+    import shutil, subprocess
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump):
+        pytest.skip("cuobjdump not available")
+    out = subprocess.run([cuobjdump, "-lelf", _build.LIB], capture_output=True, text=True).stdout
+    assert "sm_100a" in out and not re.search(r"sm_(?!100a)\d+", out), out
+
+
+def test_ctypes_structs_match_the_header_layout(pkg, tmp_path):
+    """sizeof/offsetof as the C compiler sees include/hs.h == the ctypes mirror."""
+    import subprocess
+    from cpp_optical_flow_b200 import hs_ctypes as H
+    src = tmp_path / "sz.c"
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "hs.h"\nint main(void){printf("%zu %zu %zu %zu %zu %zu\\n",'
+                   'sizeof(hs_config), sizeof(hs_timing), sizeof(hs_device_view), offsetof(hs_config, alpha),'
+                   'offsetof(hs_config, stream), offsetof(hs_device_view, halo_rows_bottom));return 0;}\n')
+    exe = tmp_path / "sz"
+    subprocess.run(["/usr/bin/gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    got = [int(x) for x in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()]
+    want = [ctypes.sizeof(H.HsConfig), ctypes.sizeof(H.HsTiming), ctypes.sizeof(H.HsDeviceView),
+            H.HsConfig.alpha.offset, H.HsConfig.stream.offset, H.HsDeviceView.halo_rows_bottom.offset]
+    assert got == want, (got, want)
+
+
+def test_create_rejects_bad_arguments_before_touching_cuda(pkg):
+    from cpp_optical_flow_b200 import hs_ctypes as H
+    lib = pkg.load_library()
+    ctx = ctypes.c_void_p()
+    cfg = H.HsConfig(struct_size=ctypes.sizeof(H.HsConfig), width=0, height=4, window_size=3, max_iterations=1, alpha=1.0)
+    assert lib.hs_create(ctypes.byref(cfg), ctypes.byref(ctx)) == 1 and not ctx.value
+    assert b"width" in lib.hs_last_error(None)
+    cfg.width = 4; cfg.window_size = 0
+    assert lib.hs_create(ctypes.byref(cfg), ctypes.byref(ctx)) == 1
+    cfg.window_size = 3; cfg.struct_size = 9999
+    assert lib.hs_create(ctypes.byref(cfg), ctypes.byref(ctx)) == 1
+    assert lib.hs_create(None, ctypes.byref(ctx)) == 1
+    assert lib.hs_solve_device(None) == 1 and lib.hs_sync(None) == 1
+    lib.hs_destroy(None)                                    # must be a no-op
+
+
+@pytest.mark.skipif(has_gpu(), reason="only meaningful on a machine without a GPU")
+def test_no_cpu_fallback(pkg):
+    from cpp_optical_flow_b200 import hs_ctypes as H
+    with pytest.raises(H.HsError) as e:
+        pkg.Solver(64, 64, 3, 10, 1.0)
+    assert e.value.status == 2 and "no CPU fallback" in str(e.value)
+    hs = pkg.hornSchunck(5, 100, 1.0)                       # constructing the mirror is free ...
+    assert (hs.windowSize, hs.maxIterations, hs.alpha) == (5, 100, 1.0)
+    with pytest.raises(H.HsError):                          # ... computing is not possible without the GPU
+        hs.getFlow(np.zeros((8, 8), np.uint8), np.zeros((8, 8), np.uint8))
+
+
+def test_product_code_never_imports_the_oracle():
+    pk = os.path.join(ROOT, "cpp-optical-flow_b200")
+    for dirpath, _, files in os.walk(pk):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
+                src = open(os.path.join(dirpath, f), errors="ignore").read()
+                assert "hs_oracle" not in src and "oracle/" not in src, os.path.join(dirpath, f)
+
+
+def test_mirror_rejects_bad_images(pkg):
+    from cpp_optical_flow_b200.horn_schunck import _as_u8_image
+    with pytest.raises(ValueError):
+        _as_u8_image(np.zeros((4, 4, 3), np.uint8), "prev")      # colour frames must be converted first
+    with pytest.raises(ValueError):
+        _as_u8_image(np.full((4, 4), 0.5), "prev")               # not representable as 8-bit
+    assert _as_u8_image(np.full((4, 4), 7.0), "prev").dtype == np.uint8
+
+
+def test_synthetic_generator_is_deterministic_and_slab_consistent(pkg):
+    s = pkg.synth
+    a, b = s.frame_pair(96, 128, seed=5)
+    a2, b2 = s.frame_pair(96, 128, seed=5)
+    assert np.array_equal(a, a2) and np.array_equal(b, b2) and a.dtype == np.uint8
+    part_a, part_b = s.frame_pair(30, 128, seed=5, y0=40)
+    assert np.array_equal(part_a, a[40:70]) and np.array_equal(part_b, b[40:70])
+    assert a.std() > 10 and not np.array_equal(a, b)

@@ -1,0 +1,254 @@
+"""GPU parity tests (run on the B200 box: pytest -m gpu).  Every call goes through the C ABI
+(libhs_b200.so via ctypes); the oracle is only the checker.
+
+Tolerances (BASELINE.json north_star): gradients bit-exact; flow max|du|,|dv| <= 1e-4 px and mean
+endpoint-error difference <= 1e-5 px against the fp64 oracle.  Invariances between kernel variants
+are bit-exact because every variant uses the same canonical arithmetic (hs_kernels.cuh)."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN
+
+pytestmark = pytest.mark.gpu
+
+TOL_MAX = 1e-4
+TOL_EPE = 1e-5
+
+
+def rand_pair(shape, seed, jitter=20):
+    rng = np.random.default_rng(seed)
+    a = rng.integers(0, 256, shape, dtype=np.uint8)
+    b = np.clip(a.astype(int) + rng.integers(-jitter, jitter + 1, shape), 0, 255).astype(np.uint8)
+    return a, b
+
+
+def assert_flow_close(u, v, ou, ov):
+    du, dv = np.abs(u - ou).max(), np.abs(v - ov).max()
+    epe = np.abs(np.hypot(u, v) - np.hypot(ou, ov)).mean()
+    assert du <= TOL_MAX and dv <= TOL_MAX, (du, dv)
+    assert epe <= TOL_EPE, epe
+
+
+# ---------------------------------------------------------------- gradients (getGradients :19-41)
+@pytest.mark.parametrize("shape", [(1, 1), (1, 7), (7, 1), (2, 3), (3, 2), (5, 5), (64, 96), (37, 131), (375, 1242)])
+def test_gradients_bit_exact_random(pkg, oracle, shape):
+    rng = np.random.default_rng(shape[0] * 1000 + shape[1])
+    a = rng.integers(0, 256, shape, dtype=np.uint8)
+    b = rng.integers(0, 256, shape, dtype=np.uint8)
+    hs = pkg.hornSchunck(3, 1, 1.0)
+    gx, gy, gt = hs.getGradients(a, b)
+    ogx, ogy, ogt = oracle.np_gradients(a, b)
+    assert gx.dtype == np.float64 and gx.shape == shape
+    assert np.array_equal(gx, ogx) and np.array_equal(gy, ogy) and np.array_equal(gt, ogt)
+    hs.close()
+
+
+def test_gradients_extreme_values_fit_the_packed_format(pkg, oracle):
+    """|Ix|,|Iy| reach 1020 and |It| 255 on black/white steps: the 11/11/10-bit packing must hold them."""
+    a = np.zeros((16, 16), np.uint8); a[:, 8:] = 255; a[8:, :] = 255 - a[8:, :]
+    b = 255 - a
+    hs = pkg.hornSchunck(3, 1, 1.0)
+    g = hs.getGradients(a, b)
+    o = oracle.np_gradients(a, b)
+    assert max(np.abs(o[0]).max(), np.abs(o[1]).max()) == 1020 and np.abs(o[2]).max() == 255
+    assert all(np.array_equal(x, y) for x, y in zip(g, o))
+    hs.close()
+
+
+@pytest.mark.parametrize("pair", ["000040", "000050"])
+def test_gradients_bit_exact_kitti(pkg, oracle, kitti, pair):
+    a, b = kitti(pair)
+    hs = pkg.hornSchunck(5, 1, 1.0)
+    g = hs.getGradients(a, b)
+    o = oracle.cv_gradients(a, b)
+    assert all(np.array_equal(x, y) for x, y in zip(g, o))
+    hs.close()
+
+
+# ---------------------------------------------------------------- flow (getFlow :43-75)
+@pytest.mark.parametrize("w", [1, 2, 3, 4, 5, 7, 8])
+@pytest.mark.parametrize("alpha", [0.5, 1.0, 10.0])
+@pytest.mark.parametrize("iters", [1, 2, 7, 100])
+def test_flow_matches_oracle(pkg, c_oracle, w, alpha, iters):
+    a, b = rand_pair((97, 150), seed=w * 100 + iters)
+    ou, ov = c_oracle.flow(a, b, w, iters, alpha)
+    hs = pkg.hornSchunck(w, iters, alpha)
+    u, v = hs.getFlow(a, b)
+    hs.close()
+    assert u.dtype == np.float64 and u.shape == a.shape
+    assert_flow_close(u, v, ou, ov)
+
+
+def test_zero_iterations_gives_zeros(pkg):
+    a, b = rand_pair((20, 30), 1)
+    hs = pkg.hornSchunck(3, 0, 1.0)
+    u, v = hs.getFlow(a, b)
+    hs.close()
+    assert not u.any() and not v.any()
+
+
+@pytest.mark.parametrize("shape", [(1, 1), (1, 7), (7, 1), (2, 3), (3, 2), (5, 5), (47, 129), (49, 121), (96, 240)])
+@pytest.mark.parametrize("w", [3, 5])
+def test_flow_edge_shapes(pkg, oracle, shape, w):
+    a, b = rand_pair(shape, seed=shape[0] * 31 + shape[1])
+    *_, ou, ov = oracle.np_flow(a, b, w, 9, 1.0)
+    hs = pkg.hornSchunck(w, 9, 1.0)
+    u, v = hs.getFlow(a, b)
+    hs.close()
+    assert_flow_close(u, v, ou, ov)
+
+
+@pytest.mark.parametrize("pair,w,iters", [("000050", 5, 100), ("000040", 5, 100), ("000050", 3, 300)])
+def test_flow_kitti_authors_run(pkg, oracle, kitti, pair, w, iters):
+    """The reference author's own configuration (main.cpp:42-43,94-96) on the bundled frames."""
+    a, b = kitti(pair)
+    *_, ou, ov = oracle.cv_flow(a, b, w, iters, 1.0)
+    hs = pkg.hornSchunck(w, iters, 1.0)
+    u, v = hs.getFlow(a, b)
+    hs.close()
+    assert np.abs(ou).max() > 50          # real-image flows are large: the hard case for fp32
+    assert_flow_close(u, v, ou, ov)
+    if w == 5 and iters == 100:
+        # ... and the GPU result draws the reference's golden plot (plotFlow.cpp restated in the oracle)
+        gold = np.load(os.path.join(GOLDEN, f"plot_{pair}.npz"))
+        canvas = np.full(a.shape + (3,), 7, np.uint8)
+        img = oracle.plot_bresenham(canvas, u, v, 20, 20.0, 5)
+        yx = gold["yx"].astype(np.int64)
+        wrong = int((img[yx[:, 0], yx[:, 1]] != gold["bgr"]).any(axis=1).sum())
+        assert wrong <= 20, wrong           # a (int) truncation may flip for a value within 1e-4 of k/20
+
+
+def test_alpha_zero_nan_pattern_matches_reference(pkg, oracle):
+    a = np.full((12, 12), 9, np.uint8)
+    b = a.copy(); b[3, 4] = 12; a[8, 8] = 200
+    *_, ou, ov = oracle.np_flow(a, b, 3, 1, 0.0)
+    hs = pkg.hornSchunck(3, 1, 0.0)
+    u, v = hs.getFlow(a, b)
+    hs.close()
+    assert np.isnan(ou).any()
+    assert np.array_equal(np.isnan(u), np.isnan(ou)) and np.array_equal(np.isnan(v), np.isnan(ov))
+    m = ~np.isnan(ou)
+    assert np.allclose(u[m], ou[m], atol=1e-4) and np.allclose(v[m], ov[m], atol=1e-4)
+
+
+# ---------------------------------------------------------------- invariances (bit-exact)
+@pytest.mark.parametrize("w,k", [(3, 1), (3, 2), (3, 3), (3, 4), (3, 7), (3, 12), (5, 1), (5, 2), (5, 3), (5, 5),
+                                 (2, 4), (2, 9), (4, 2), (4, 3)])
+def test_fused_kernel_equals_generic_sweep(pkg, w, k):
+    from cpp_optical_flow_b200 import hs_ctypes as H
+    a, b = rand_pair((333, 517), seed=w * 10 + k)
+    iters = 2 * k + 1                      # full launches plus a remainder launch
+    with pkg.Solver(517, 333, w, iters, 1.0, flags=H.FLAG_FORCE_GENERIC) as s:
+        gu, gv = s.solve(a, b, np.float32)
+        assert s.timing().kernel_id == 0
+    with pkg.Solver(517, 333, w, iters, 1.0, temporal_k=k) as s:
+        tu, tv = s.solve(a, b, np.float32)
+        assert s.timing().kernel_id == 1 and s.timing().temporal_k == k
+    assert np.array_equal(gu, tu) and np.array_equal(gv, tv)
+
+
+def test_iterate_is_a_semigroup_and_deterministic(pkg):
+    a, b = rand_pair((211, 390), 5)
+    with pkg.Solver(390, 211, 3, 50, 1.0) as s:
+        s.upload(a, b); s.prepare(); s.iterate(50); u1, v1 = s.download(np.float32)
+        s.prepare(); s.iterate(13); s.iterate(4); s.iterate(33); u2, v2 = s.download(np.float32)
+        s.solve_device(); u3, v3 = s.download(np.float32)
+    assert np.array_equal(u1, u2) and np.array_equal(v1, v2) and np.array_equal(u1, u3) and np.array_equal(v1, v3)
+
+
+def test_batch_equals_single_solves(pkg):
+    pairs = [rand_pair((120, 200), 40 + i) for i in range(3)]
+    prev = np.stack([p[0] for p in pairs]); nxt = np.stack([p[1] for p in pairs])
+    with pkg.Solver(200, 120, 3, 21, 1.0, batch=3) as s:
+        bu, bv = s.solve(prev, nxt, np.float32)
+    for i, (a, b) in enumerate(pairs):
+        with pkg.Solver(200, 120, 3, 21, 1.0) as s:
+            u, v = s.solve(a, b, np.float32)
+        assert np.array_equal(bu[i], u) and np.array_equal(bv[i], v)
+
+
+def test_strided_inputs(pkg):
+    big_a, big_b = rand_pair((90, 300), 9)
+    a, b = big_a[:, 10:210], big_b[:, 10:210]            # row stride 300, width 200
+    assert not a.flags.c_contiguous
+    hs = pkg.hornSchunck(3, 11, 1.0)
+    u1, v1 = hs.getFlow(a, b)
+    u2, v2 = hs.getFlow(np.ascontiguousarray(a), np.ascontiguousarray(b))
+    hs.close()
+    assert np.array_equal(u1, u2) and np.array_equal(v1, v2)
+
+
+def test_f32_and_f64_outputs_agree(pkg):
+    a, b = rand_pair((64, 80), 2)
+    with pkg.Solver(80, 64, 5, 15, 1.0) as s:
+        u64, v64 = s.solve(a, b, np.float64)
+        u32, v32 = s.solve(a, b, np.float32)
+    assert np.array_equal(u64, u32.astype(np.float64)) and np.array_equal(v64, v32.astype(np.float64))
+
+
+# ---------------------------------------------------------------- row slabs (one context per slab)
+@pytest.mark.parametrize("w,k,nslab", [(3, 4, 2), (3, 3, 3), (5, 2, 2), (4, 2, 3), (3, 1, 4)])
+def test_row_slabs_equal_single_solve(pkg, w, k, nslab):
+    """N slab contexts on one GPU with host-side halo copies == one whole-image solve, bit for bit."""
+    from cpp_optical_flow_b200 import slab
+    a, b = rand_pair((260, 300), seed=w + k)
+    iters = 3 * k + 2
+    with pkg.Solver(300, 260, w, iters, 1.0, temporal_k=k) as s:
+        u, v = s.solve(a, b, np.float32)
+    su, sv = slab.solve_slabs_single_process(a, b, w, iters, 1.0, nslab, temporal_k=k)
+    assert np.array_equal(u, su) and np.array_equal(v, sv)
+
+
+# ---------------------------------------------------------------- BASELINE configs at full size
+@pytest.mark.parametrize("w", [3, 5])
+def test_config2_1080p_full_size(pkg, c_oracle, w):
+    """configs[1]: 1920x1080, alpha=1, 1000 sweeps.  Oracle at full size for 60 sweeps (seconds on one
+    core); at 1000 sweeps size-independent properties: fused == generic bit-exact, known translation."""
+    from cpp_optical_flow_b200 import hs_ctypes as H, synth
+    a, b = synth.frame_pair(1080, 1920)
+    ou, ov = c_oracle.flow(a, b, w, 60, 1.0)
+    with pkg.Solver(1920, 1080, w, 60, 1.0) as s:
+        u, v = s.solve(a, b, np.float64)
+    assert_flow_close(u, v, ou, ov)
+    with pkg.Solver(1920, 1080, w, 1000, 1.0) as s:
+        u, v = s.solve(a, b, np.float32)
+    with pkg.Solver(1920, 1080, w, 1000, 1.0, flags=H.FLAG_FORCE_GENERIC) as s:
+        gu, gv = s.solve(a, b, np.float32)
+    assert np.array_equal(u, gu) and np.array_equal(v, gv)
+    # the pair is a pure translation by (1.0, 0.5) px; flow is in units of px/8 (unnormalised Sobel)
+    assert abs(np.median(u) - 1.0 / 8) < 0.01 and abs(np.median(v) - 0.5 / 8) < 0.01
+
+
+def test_config3_4k_crop_oracle(pkg, oracle):
+    """configs[2] size (3840x2160): a crop oracle with margin r*T+1 must match the interior exactly enough."""
+    from cpp_optical_flow_b200 import synth
+    a, b = synth.frame_pair(2160, 3840)
+    w, iters = 3, 40
+    with pkg.Solver(3840, 2160, w, iters, 1.0) as s:
+        u, v = s.solve(a, b, np.float64)
+    m = oracle.crop_margin(w, iters)
+    for (y0, x0) in ((0, 0), (1000, 1900), (2160 - 64, 3840 - 64)):
+        ya, yb, xa, xb = max(0, y0 - m), min(2160, y0 + 64 + m), max(0, x0 - m), min(3840, x0 + 64 + m)
+        *_, cu, cv_ = oracle.cv_flow(a[ya:yb, xa:xb], b[ya:yb, xa:xb], w, iters, 1.0)
+        sl = (slice(y0 - ya, y0 - ya + 64), slice(x0 - xa, x0 - xa + 64))
+        assert_flow_close(u[y0:y0 + 64, x0:x0 + 64], v[y0:y0 + 64, x0:x0 + 64], cu[sl], cv_[sl])
+
+
+# ---------------------------------------------------------------- error behaviour
+def test_argument_errors(pkg):
+    from cpp_optical_flow_b200 import hs_ctypes as H
+    with pytest.raises(H.HsError) as e:
+        pkg.Solver(0, 10, 3, 1, 1.0)
+    assert e.value.status == 1
+    with pytest.raises(H.HsError):
+        pkg.Solver(10, 10, 0, 1, 1.0)
+    with pytest.raises(H.HsError):
+        pkg.Solver(10, 10, 3, -1, 1.0)
+    with pkg.Solver(32, 16, 3, 1, 1.0) as s:
+        with pytest.raises(ValueError):                      # main.cpp:70-73: sizes must agree
+            s.solve(np.zeros((16, 32), np.uint8), np.zeros((16, 31), np.uint8))
+        with pytest.raises(H.HsError) as e:
+            s.iterate(1)                                     # nothing uploaded / prepared yet
+        assert e.value.status == 5
