@@ -65,6 +65,7 @@ struct hs_ctx {
 
     CUtensorMap tm_u[2], tm_v[2], tm_cpk, tm_inv;
     int kernel_id = 0;  // 0 generic, 1 fused tile
+    int num_sms = 148;
     int k = 1;
 
     cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -143,14 +144,20 @@ struct Tile {
     }
     static int max_k() { return (TS::SY - 1) / std::max(1, RL + RR); }
     static cudaError_t launch(hs_ctx* c, int kk) {
-        const int hxl = round_up(RL * kk, 4), hxr = round_up(RR * kk, 4);
-        const int hyt = RL * kk, hyb = RR * kk;
-        const int vx = TS::SX - hxl - hxr, vy = TS::SY - hyt - hyb;
-        dim3 grid((c->W + vx - 1) / vx, (c->oy1 - c->oy0 + vy - 1) / vy, c->B);
+        hs::TileGrid tg;
+        tg.k = kk;
+        tg.hxl = round_up(RL * kk, 4);
+        tg.hyt = RL * kk;
+        tg.vx = TS::SX - tg.hxl - round_up(RR * kk, 4);
+        tg.vy = TS::SY - tg.hyt - RR * kk;
+        tg.tiles_x = (c->W + tg.vx - 1) / tg.vx;
+        tg.tiles_y = (c->oy1 - c->oy0 + tg.vy - 1) / tg.vy;
+        tg.ntiles = tg.tiles_x * tg.tiles_y * c->B;
+        const int grid = std::min(tg.ntiles, c->num_sms);      // persistent: one CTA per SM
         const float kf = 1.0f / (float)(c->w * c->w);
         kernel()<<<grid, TS::THREADS, TS::SMEM, c->stream>>>(
             c->tm_u[c->cur], c->tm_v[c->cur], c->tm_cpk, c->tm_inv, c->d_u[c->cur ^ 1],
-            c->d_v[c->cur ^ 1], c->geom(), kk, hxl, hyt, vx, vy, kf);
+            c->d_v[c->cur ^ 1], c->geom(), tg, kf);
         return cudaGetLastError();
     }
 };
@@ -356,6 +363,7 @@ int hs_create(const hs_config* cfg_in, hs_ctx** out) {
     cudaDeviceProp prop;
     if ((e = cudaGetDeviceProperties(&prop, dev)) != cudaSuccess)
         return bail(fail(c, HS_ERR_CUDA, "cudaGetDeviceProperties: %s", cudaGetErrorString(e)));
+    c->num_sms = prop.multiProcessorCount;
     if (prop.major < 10)
         return bail(fail(c, HS_ERR_UNSUPPORTED, "device %d is sm_%d%d; this library is built for sm_100a (B200) only",
                          dev, prop.major, prop.minor));
@@ -401,7 +409,7 @@ int hs_create(const hs_config* cfg_in, hs_ctx** out) {
     if (have_tile) {
         using TS0 = hs::TileShape<1, 1, TILE_R, TILE_NWARP>;
         int k = cfg.temporal_k > 0 ? cfg.temporal_k : env_int("HS_K", 0);
-        if (k <= 0) k = std::max(1, 4 / std::max(1, std::max(c->RL, c->RR)));   // w=3: 4, w=5: 2
+        if (k <= 0) k = std::max(1, 6 / std::max(1, std::max(c->RL, c->RR)));   // measured on B200: w=3 -> 6, w=5 -> 3
         k = std::min(k, kmax);
         // keep a useful centre: at least a quarter of the staged rows must be output rows
         while (k > 1 && TS0::SY - (c->RL + c->RR) * k < TS0::SY / 4) --k;

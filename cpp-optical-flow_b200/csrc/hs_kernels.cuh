@@ -207,15 +207,18 @@ __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
 }
 
 // ------------------------------------------------------------------------------------------
-// K3: k fused Jacobi sweeps per launch.
+// K3: k fused Jacobi sweeps per launch (temporal blocking), persistent CTAs.
 //
-// One CTA owns a staged tile of SX x SY pixels (SX = 128 = 32 lanes x 4 px, SY = NWARP x R rows).
-// Four TMA boxes (u, v, packed Ix/Iy/It, inv) land in shared memory; each thread then keeps its
-// 4 x R patch of u, v AND its coefficients in registers for all k sweeps.  Per sweep:
-//   1. row sums of the patch, horizontal neighbours by warp shuffle
-//   2. the patch's top/bottom row sums go to a double-buffered shared exchange array
-//   3. one __syncthreads
-//   4. rows of the vertical neighbours come back from shared memory, box sum, update in place
+// One CTA per SM walks over staged tiles of SX x SY pixels (SX = 128 = 32 lanes x 4 px,
+// SY = NWARP x R rows), tile = blockIdx.x, blockIdx.x + gridDim.x, ...  Per tile:
+//   * four TMA boxes (u, v, packed Ix/Iy/It, inv) land in one of TWO shared-memory stages; the
+//     boxes of the NEXT tile are issued as soon as this tile's registers are loaded, so they
+//     stream in underneath the k sweeps of this tile (mbarrier full[stage], parity = use count)
+//   * each thread keeps its 4 x R patch of u, v AND its coefficients in registers for all k sweeps
+//   * per sweep: (1) row sums of the patch, horizontal neighbours by warp shuffle; (2) the rows a
+//     vertical neighbour needs go to a double-buffered exchange array (it lives in the stage the
+//     tile came from, which is dead once the registers are loaded); (3) one __syncthreads;
+//     (4) neighbour rows come back, box sum, update in place
 // The ring of pixels whose dependency cone leaves the staged tile grows by (a, w/2) per sweep,
 // so after k sweeps the centre VX x VY pixels are exact and are the only ones stored.
 // Pixels outside the image must be 0 at EVERY sweep (BORDER_CONSTANT): TMA zero-fill gives that
@@ -223,20 +226,28 @@ __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
 // ------------------------------------------------------------------------------------------
 template <int RL, int RR, int R, int NWARP>
 struct TileShape {
+    static_assert(RL <= R && RR <= R, "a thread's vertical neighbours are the adjacent patches only");
     static constexpr int SX = 128;
     static constexpr int SY = NWARP * R;
     static constexpr int THREADS = NWARP * 32;
-    static constexpr int EXROWS = SY + RL + RR;                       // exchange rows incl. zero pads
+    static constexpr int NSLOT = (RL + RR < R) ? (RL + RR) : R;       // patch rows a neighbour reads
     static constexpr size_t BYTES_F32 = (size_t)SX * SY * 4;
-    static constexpr size_t OFF_U = 0;
+    static constexpr size_t OFF_U = 0;                                // offsets inside one stage
     static constexpr size_t OFF_V = OFF_U + BYTES_F32;
     static constexpr size_t OFF_CPK = OFF_V + BYTES_F32;
     static constexpr size_t OFF_INV = OFF_CPK + BYTES_F32;
-    static constexpr size_t OFF_EX = OFF_INV + BYTES_F32;             // [2 buf][2 field][EXROWS][SX]
-    static constexpr size_t BYTES_EX = (size_t)2 * 2 * EXROWS * SX * 4;
-    static constexpr size_t OFF_BAR = OFF_EX + BYTES_EX;
+    static constexpr size_t STAGE = OFF_INV + BYTES_F32;
+    // exchange array [2 buf][2 field][NWARP][NSLOT][SX] floats, aliased onto the consumed stage
+    static constexpr size_t EX_FIELD = (size_t)NWARP * NSLOT * SX;    // floats
+    static constexpr size_t BYTES_EX = 2 * 2 * EX_FIELD * 4;
+    static_assert(BYTES_EX <= STAGE, "exchange array must fit in one stage");
+    static constexpr size_t OFF_BAR = 2 * STAGE;
     static constexpr size_t SMEM = OFF_BAR + 16;
-    static constexpr uint32_t TX_BYTES = (uint32_t)(4 * BYTES_F32);
+    static constexpr uint32_t TX_BYTES = (uint32_t)STAGE;
+    // slot of patch row j in the exchange array (-1: no neighbour reads it)
+    __host__ __device__ static constexpr int slot(int j) {
+        return (RL + RR >= R) ? j : (j < RR ? j : (j >= R - RL ? RR + (j - (R - RL)) : -1));
+    }
 };
 
 // row sums of one patch row: 4 outputs from 4 own values + RL left + RR right neighbours
@@ -262,42 +273,44 @@ template <int RL, int RR, int R, int NWARP, bool MASKED>
 __device__ __forceinline__ void tile_sweeps(float (&u)[R][4], float (&v)[R][4],
                                             const float (&ix)[R][4], const float (&iy)[R][4],
                                             const float (&it)[R][4], const float (&iv)[R][4],
-                                            float* ex, int k, float kf, int row0, int lane,
+                                            float* ex, int k, float kf, int warp, int lane,
                                             uint32_t inmask) {
     using TS = TileShape<RL, RR, R, NWARP>;
+    // the patches above / below; at the tile's top and bottom there is none: those rows only feed
+    // pixels of the invalid ring, so any finite-or-not value will do - read our own slots
+    const int wa = warp > 0 ? warp - 1 : 0;
+    const int wb = warp < NWARP - 1 ? warp + 1 : NWARP - 1;
     for (int s = 0; s < k; ++s) {
-        float* exu = ex + (size_t)(s & 1) * 2 * TS::EXROWS * TS::SX;
-        float* exv = exu + (size_t)TS::EXROWS * TS::SX;
+        float* exu = ex + (size_t)(s & 1) * 2 * TS::EX_FIELD;
+        float* exv = exu + TS::EX_FIELD;
         float hu[R][4], hv[R][4];
 #pragma unroll
         for (int j = 0; j < R; ++j) {
             row_sums<RL, RR>(u[j], hu[j]);
             row_sums<RL, RR>(v[j], hv[j]);
-            if (j < RR || j >= R - RL) {  // rows a vertical neighbour will need
-                const int er = row0 + j + RL;
-                *reinterpret_cast<float4*>(exu + (size_t)er * TS::SX + lane * 4) =
-                    make_float4(hu[j][0], hu[j][1], hu[j][2], hu[j][3]);
-                *reinterpret_cast<float4*>(exv + (size_t)er * TS::SX + lane * 4) =
-                    make_float4(hv[j][0], hv[j][1], hv[j][2], hv[j][3]);
+            if (TS::slot(j) >= 0) {  // rows a vertical neighbour will need
+                const size_t o = ((size_t)warp * TS::NSLOT + TS::slot(j)) * TS::SX + lane * 4;
+                *reinterpret_cast<float4*>(exu + o) = make_float4(hu[j][0], hu[j][1], hu[j][2], hu[j][3]);
+                *reinterpret_cast<float4*>(exv + o) = make_float4(hv[j][0], hv[j][1], hv[j][2], hv[j][3]);
             }
         }
         __syncthreads();
-        // neighbour rows: tile rows row0-RL .. row0-1 (above) and row0+R .. row0+R+RR-1 (below)
+        // neighbour rows: the last RL rows of the patch above, the first RR rows of the patch below
         float au[RL > 0 ? RL : 1][4], av[RL > 0 ? RL : 1][4];
         float bu[RR > 0 ? RR : 1][4], bv[RR > 0 ? RR : 1][4];
 #pragma unroll
         for (int i = 0; i < RL; ++i) {
-            const int er = row0 - RL + i + RL;
-            const float4 q = *reinterpret_cast<const float4*>(exu + (size_t)er * TS::SX + lane * 4);
-            const float4 p = *reinterpret_cast<const float4*>(exv + (size_t)er * TS::SX + lane * 4);
+            const size_t o = ((size_t)wa * TS::NSLOT + TS::slot(R - RL + i)) * TS::SX + lane * 4;
+            const float4 q = *reinterpret_cast<const float4*>(exu + o);
+            const float4 p = *reinterpret_cast<const float4*>(exv + o);
             au[i][0] = q.x; au[i][1] = q.y; au[i][2] = q.z; au[i][3] = q.w;
             av[i][0] = p.x; av[i][1] = p.y; av[i][2] = p.z; av[i][3] = p.w;
         }
 #pragma unroll
         for (int i = 0; i < RR; ++i) {
-            const int er = row0 + R + i + RL;
-            const float4 q = *reinterpret_cast<const float4*>(exu + (size_t)er * TS::SX + lane * 4);
-            const float4 p = *reinterpret_cast<const float4*>(exv + (size_t)er * TS::SX + lane * 4);
+            const size_t o = ((size_t)wb * TS::NSLOT + TS::slot(i)) * TS::SX + lane * 4;
+            const float4 q = *reinterpret_cast<const float4*>(exu + o);
+            const float4 p = *reinterpret_cast<const float4*>(exv + o);
             bu[i][0] = q.x; bu[i][1] = q.y; bu[i][2] = q.z; bu[i][3] = q.w;
             bv[i][0] = p.x; bv[i][1] = p.y; bv[i][2] = p.z; bv[i][3] = p.w;
         }
@@ -330,109 +343,134 @@ __device__ __forceinline__ void tile_sweeps(float (&u)[R][4], float (&v)[R][4],
     }
 }
 
+// geometry of one launch (host-computed, same for every tile)
+struct TileGrid {
+    int k;                 // sweeps fused in this launch
+    int hxl, hyt;          // halo columns left / rows above the stored centre
+    int vx, vy;            // stored centre of a tile
+    int tiles_x, tiles_y;  // tiles per image
+    int ntiles;            // tiles_x * tiles_y * batch
+};
+
 template <int RL, int RR, int R, int NWARP>
 __global__ void __launch_bounds__(NWARP * 32, 1)
 k_jacobi_tile(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CUtensorMap tm_v,
               const __grid_constant__ CUtensorMap tm_cpk, const __grid_constant__ CUtensorMap tm_inv,
-              float* __restrict__ un, float* __restrict__ vn, Geom g,
-              int k, int hxl, int hyt, int vx, int vy, float kf) {
+              float* __restrict__ un, float* __restrict__ vn, Geom g, TileGrid tg, float kf) {
     using TS = TileShape<RL, RR, R, NWARP>;
     static_assert(R * 4 <= 32, "in-image mask is one 32-bit word per thread");
     static_assert(RL <= 4 && RR <= 4, "horizontal neighbours come from the adjacent lane only");
     extern __shared__ __align__(128) unsigned char smem[];
-    float* s_u = reinterpret_cast<float*>(smem + TS::OFF_U);
-    float* s_v = reinterpret_cast<float*>(smem + TS::OFF_V);
-    uint32_t* s_cpk = reinterpret_cast<uint32_t*>(smem + TS::OFF_CPK);
-    float* s_inv = reinterpret_cast<float*>(smem + TS::OFF_INV);
-    float* s_ex = reinterpret_cast<float*>(smem + TS::OFF_EX);
-    uint64_t* bar = reinterpret_cast<uint64_t*>(smem + TS::OFF_BAR);
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem + TS::OFF_BAR);   // full[2]
 
     const int tid = threadIdx.x;
     const int lane = tid & 31;
     const int warp = tid >> 5;
-    const int b = blockIdx.z;
-    const int tx0 = blockIdx.x * vx - hxl;            // staged tile origin (may be negative)
-    const int ty0 = g.oy0 + blockIdx.y * vy - hyt;
+    const int row0 = warp * R;                        // first tile row of this thread's patch
+    const int per_img = tg.tiles_x * tg.tiles_y;
+
+    // Start coordinates are multiples of 4 floats = 16 B: UTMALDG faults ("illegal instruction")
+    // on sm_100a when the innermost start offset is not 16-byte aligned (measured, tools/tma_probe.cu).
+    auto issue_tile = [&](int t, int stage) {
+        const int b = t / per_img;
+        const int r = t - b * per_img;
+        const int by = r / tg.tiles_x;
+        const int bx = r - by * tg.tiles_x;
+        const int x0 = bx * tg.vx - tg.hxl;
+        const int y0 = g.oy0 + by * tg.vy - tg.hyt;
+        unsigned char* st = smem + (size_t)stage * TS::STAGE;
+        mbar_expect_tx(&bar[stage], TS::TX_BYTES);
+        tma_load_3d(st + TS::OFF_U, &tm_u, &bar[stage], x0, y0, b);
+        tma_load_3d(st + TS::OFF_V, &tm_v, &bar[stage], x0, y0, b);
+        tma_load_3d(st + TS::OFF_CPK, &tm_cpk, &bar[stage], x0, y0, b);
+        tma_load_3d(st + TS::OFF_INV, &tm_inv, &bar[stage], x0, y0, b);
+    };
 
     if (tid == 0) {
         tma_prefetch_desc(&tm_u);
         tma_prefetch_desc(&tm_v);
         tma_prefetch_desc(&tm_cpk);
         tma_prefetch_desc(&tm_inv);
-        mbar_init(bar, 1);
+        mbar_init(&bar[0], 1);
+        mbar_init(&bar[1], 1);
         fence_mbar_init();
+        if ((int)blockIdx.x < tg.ntiles) issue_tile(blockIdx.x, 0);
     }
     __syncthreads();
-    // Start coordinates are multiples of 4 floats = 16 B: UTMALDG faults ("illegal instruction")
-    // on sm_100a when the innermost start offset is not 16-byte aligned (measured, tools/tma_probe.cu).
-    if (tid == 0) {
-        mbar_expect_tx(bar, TS::TX_BYTES);
-        tma_load_3d(s_u, &tm_u, bar, tx0, ty0, b);
-        tma_load_3d(s_v, &tm_v, bar, tx0, ty0, b);
-        tma_load_3d(s_cpk, &tm_cpk, bar, tx0, ty0, b);
-        tma_load_3d(s_inv, &tm_inv, bar, tx0, ty0, b);
-    }
-    // while the boxes are in flight: zero the exchange pad rows (above row 0 / below row SY-1)
-    for (int i = tid; i < 2 * 2 * (RL + RR) * TS::SX; i += TS::THREADS) {
-        const int col = i % TS::SX;
-        const int pr = (i / TS::SX) % (RL + RR);
-        const int fb = i / (TS::SX * (RL + RR));      // buf*2 + field
-        const int er = (pr < RL) ? pr : (TS::SY + RL + (pr - RL));
-        s_ex[((size_t)fb * TS::EXROWS + er) * TS::SX + col] = 0.f;
-    }
 
-    const int row0 = warp * R;                        // first tile row of this thread's patch
-    const int gx0 = tx0 + lane * 4;
-    const int gy0 = ty0 + row0;
-    // which of the patch pixels lie inside the image (bit j*4+c)
-    uint32_t inmask = 0;
+    int it_no = 0;
+    for (int t = blockIdx.x; t < tg.ntiles; t += gridDim.x, ++it_no) {
+        const int stage = it_no & 1;
+        unsigned char* st = smem + (size_t)stage * TS::STAGE;
+        const float* s_u = reinterpret_cast<const float*>(st + TS::OFF_U);
+        const float* s_v = reinterpret_cast<const float*>(st + TS::OFF_V);
+        const uint32_t* s_cpk = reinterpret_cast<const uint32_t*>(st + TS::OFF_CPK);
+        const float* s_inv = reinterpret_cast<const float*>(st + TS::OFF_INV);
+
+        const int b = t / per_img;
+        const int r = t - b * per_img;
+        const int by = r / tg.tiles_x;
+        const int bx = r - by * tg.tiles_x;
+        const int tx0 = bx * tg.vx - tg.hxl;          // staged tile origin (may be negative)
+        const int ty0 = g.oy0 + by * tg.vy - tg.hyt;
+        const int gx0 = tx0 + lane * 4;
+        const int gy0 = ty0 + row0;
+        // which of the patch pixels lie inside the image (bit j*4+c)
+        uint32_t inmask = 0;
 #pragma unroll
-    for (int j = 0; j < R; ++j)
+        for (int j = 0; j < R; ++j)
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-            const bool in = (gy0 + j >= 0) && (gy0 + j < g.H) && (gx0 + c >= 0) && (gx0 + c < g.W);
-            inmask |= (in ? 1u : 0u) << (j * 4 + c);
-        }
-    const bool tile_inside = (tx0 >= 0) && (tx0 + TS::SX <= g.W) && (ty0 >= 0) && (ty0 + TS::SY <= g.H);
+            for (int c = 0; c < 4; ++c) {
+                const bool in = (gy0 + j >= 0) && (gy0 + j < g.H) && (gx0 + c >= 0) && (gx0 + c < g.W);
+                inmask |= (in ? 1u : 0u) << (j * 4 + c);
+            }
+        const bool tile_inside = (tx0 >= 0) && (tx0 + TS::SX <= g.W) && (ty0 >= 0) && (ty0 + TS::SY <= g.H);
 
-    mbar_wait(bar, 0);
+        mbar_wait(&bar[stage], (it_no >> 1) & 1);
 
-    float u[R][4], v[R][4], ix[R][4], iy[R][4], it[R][4], iv[R][4];
-#pragma unroll
-    for (int j = 0; j < R; ++j) {
-        const int so = (row0 + j) * TS::SX + lane * 4;
-        const float4 qu = *reinterpret_cast<const float4*>(s_u + so);
-        const float4 qv = *reinterpret_cast<const float4*>(s_v + so);
-        const float4 qi = *reinterpret_cast<const float4*>(s_inv + so);
-        const uint4 qc = *reinterpret_cast<const uint4*>(s_cpk + so);
-        u[j][0] = qu.x; u[j][1] = qu.y; u[j][2] = qu.z; u[j][3] = qu.w;
-        v[j][0] = qv.x; v[j][1] = qv.y; v[j][2] = qv.z; v[j][3] = qv.w;
-        iv[j][0] = qi.x; iv[j][1] = qi.y; iv[j][2] = qi.z; iv[j][3] = qi.w;
-        unpack_coef(qc.x, ix[j][0], iy[j][0], it[j][0]);
-        unpack_coef(qc.y, ix[j][1], iy[j][1], it[j][1]);
-        unpack_coef(qc.z, ix[j][2], iy[j][2], it[j][2]);
-        unpack_coef(qc.w, ix[j][3], iy[j][3], it[j][3]);
-    }
-    __syncthreads();  // exchange pad rows are zeroed before anyone reads them
-
-    if (tile_inside)
-        tile_sweeps<RL, RR, R, NWARP, false>(u, v, ix, iy, it, iv, s_ex, k, kf, row0, lane, inmask);
-    else
-        tile_sweeps<RL, RR, R, NWARP, true>(u, v, ix, iy, it, iv, s_ex, k, kf, row0, lane, inmask);
-
-    // store the exact centre of the tile
-    const int lx = lane * 4;
-    if (lx >= hxl && lx < hxl + vx && gx0 < g.W) {
-        float* U = un + (size_t)b * g.plane;
-        float* V = vn + (size_t)b * g.plane;
+        float u[R][4], v[R][4], ix[R][4], iy[R][4], it[R][4], iv[R][4];
 #pragma unroll
         for (int j = 0; j < R; ++j) {
-            const int ly = row0 + j;
-            const int gy = gy0 + j;
-            if (ly >= hyt && ly < hyt + vy && gy < g.oy1) {
-                const size_t o = (size_t)gy * g.pitch + gx0;
-                *reinterpret_cast<float4*>(U + o) = make_float4(u[j][0], u[j][1], u[j][2], u[j][3]);
-                *reinterpret_cast<float4*>(V + o) = make_float4(v[j][0], v[j][1], v[j][2], v[j][3]);
+            const int so = (row0 + j) * TS::SX + lane * 4;
+            const float4 qu = *reinterpret_cast<const float4*>(s_u + so);
+            const float4 qv = *reinterpret_cast<const float4*>(s_v + so);
+            const float4 qi = *reinterpret_cast<const float4*>(s_inv + so);
+            const uint4 qc = *reinterpret_cast<const uint4*>(s_cpk + so);
+            u[j][0] = qu.x; u[j][1] = qu.y; u[j][2] = qu.z; u[j][3] = qu.w;
+            v[j][0] = qv.x; v[j][1] = qv.y; v[j][2] = qv.z; v[j][3] = qv.w;
+            iv[j][0] = qi.x; iv[j][1] = qi.y; iv[j][2] = qi.z; iv[j][3] = qi.w;
+            unpack_coef(qc.x, ix[j][0], iy[j][0], it[j][0]);
+            unpack_coef(qc.y, ix[j][1], iy[j][1], it[j][1]);
+            unpack_coef(qc.z, ix[j][2], iy[j][2], it[j][2]);
+            unpack_coef(qc.w, ix[j][3], iy[j][3], it[j][3]);
+        }
+        // Everyone has (a) finished the previous tile - its exchange scratch in the OTHER stage is
+        // dead - and (b) pulled this tile out of THIS stage, which now becomes the exchange scratch.
+        fence_proxy_async();      // our generic-proxy scratch accesses of the other stage, before TMA rewrites it
+        __syncthreads();
+        if (tid == 0 && t + (int)gridDim.x < tg.ntiles)
+            issue_tile(t + gridDim.x, stage ^ 1);     // lands underneath this tile's k sweeps
+
+        float* s_ex = reinterpret_cast<float*>(st);
+        if (tile_inside)
+            tile_sweeps<RL, RR, R, NWARP, false>(u, v, ix, iy, it, iv, s_ex, tg.k, kf, warp, lane, inmask);
+        else
+            tile_sweeps<RL, RR, R, NWARP, true>(u, v, ix, iy, it, iv, s_ex, tg.k, kf, warp, lane, inmask);
+
+        // store the exact centre of the tile
+        const int lx = lane * 4;
+        if (lx >= tg.hxl && lx < tg.hxl + tg.vx && gx0 < g.W) {
+            float* U = un + (size_t)b * g.plane;
+            float* V = vn + (size_t)b * g.plane;
+#pragma unroll
+            for (int j = 0; j < R; ++j) {
+                const int ly = row0 + j;
+                const int gy = gy0 + j;
+                if (ly >= tg.hyt && ly < tg.hyt + tg.vy && gy < g.oy1) {
+                    const size_t o = (size_t)gy * g.pitch + gx0;
+                    *reinterpret_cast<float4*>(U + o) = make_float4(u[j][0], u[j][1], u[j][2], u[j][3]);
+                    *reinterpret_cast<float4*>(V + o) = make_float4(v[j][0], v[j][1], v[j][2], v[j][3]);
+                }
             }
         }
     }

@@ -229,7 +229,7 @@ def bench_slab(args, rank, local_rank, world, metric, algo_bytes, peak_fn):
     T = args.iters or 5000
     window = args.window
     rl, rr = radii(window)
-    k = args.k or max(1, 4 // max(1, max(rl, rr)))
+    k = args.k or max(1, 6 // max(1, max(rl, rr)))
     geom = plan(H, W, world, rank, window, k)
     dev = torch.device("cuda", local_rank)
     prev, nxt = synth.frame_pair(geom.f1 - geom.f0, W, y0=geom.f0)
