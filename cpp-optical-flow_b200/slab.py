@@ -124,19 +124,23 @@ class _DevMem:
 class DeviceSlab:
     """One rank's slab on its GPU: an hs_ctx sized for band + halo, plus torch views of u, v."""
 
-    def __init__(self, geom: SlabGeometry, iterations: int, alpha: float, device: int, stream=None):
+    def __init__(self, geom: SlabGeometry, iterations: int, alpha: float, device: int):
         import torch
         from . import hs_ctypes as H
         from .horn_schunck import Solver
         self.geom, self.iterations = geom, iterations
+        self._torch = torch
+        self._device = torch.device("cuda", device)
+        # One explicit stream carries the kernels AND is torch's current stream around the NCCL
+        # send/recv, so launches and halo exchanges are ordered on the device without host syncs.
+        # (A NULL stream in hs_config means "private stream", so the default stream cannot be used.)
+        self.stream = torch.cuda.Stream(device=self._device)
         flags = (H.FLAG_TOP_IS_SEAM if geom.top_seam else 0) | (H.FLAG_BOTTOM_IS_SEAM if geom.bottom_seam else 0)
         self.solver = Solver(geom.width, geom.rows, geom.window, iterations, alpha, device=device,
-                             temporal_k=geom.k, flags=flags, out_rows=geom.out_rows, stream=stream)
+                             temporal_k=geom.k, flags=flags, out_rows=geom.out_rows, stream=self.stream.cuda_stream)
         self.k = self.solver.timing().temporal_k
         if self.k != geom.k:
             raise ValueError(f"library chose k={self.k}, slab plan was made for k={geom.k}")
-        self._torch = torch
-        self._device = torch.device("cuda", device)
         self._views = {}
 
     def close(self):
@@ -158,17 +162,19 @@ class DeviceSlab:
         return out
 
     def run(self, exchange=exchange_halos, group=None):
-        """prepare + `iterations` sweeps, exchanging halos after every fused launch but the last."""
-        self.solver.prepare()
-        left = self.iterations
+        """prepare + `iterations` sweeps, exchanging halos after every fused launch but the last.
+        Asynchronous: everything is queued on self.stream."""
         launches = 0
-        while left > 0:
-            kk = min(self.k, left)
-            self.solver.iterate(kk)
-            left -= kk
-            launches += 1
-            if left > 0 and self.geom.world > 1:
-                exchange(self.geom, self.planes(), group)
+        with self._torch.cuda.stream(self.stream):
+            self.solver.prepare()
+            left = self.iterations
+            while left > 0:
+                kk = min(self.k, left)
+                self.solver.iterate(kk)
+                left -= kk
+                launches += 1
+                if left > 0 and self.geom.world > 1:
+                    exchange(self.geom, self.planes(), group)
         return launches
 
     def download(self, dtype=np.float32):
@@ -233,7 +239,7 @@ def bench_slab(args, rank, local_rank, world, metric, algo_bytes, peak_fn):
     geom = plan(H, W, world, rank, window, k)
     dev = torch.device("cuda", local_rank)
     prev, nxt = synth.frame_pair(geom.f1 - geom.f0, W, y0=geom.f0)
-    slab = DeviceSlab(geom, T, 1.0, local_rank, stream=torch.cuda.current_stream().cuda_stream)
+    slab = DeviceSlab(geom, T, 1.0, local_rank)
     slab.upload(prev, nxt)
     slab.solver.sync()
     flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
@@ -252,11 +258,12 @@ def bench_slab(args, rank, local_rank, world, metric, algo_bytes, peak_fn):
     barrier(); torch.cuda.synchronize()
     wall0 = time.perf_counter()
     for s, e in ev:
-        flush.zero_()
-        barrier()
-        s.record()
+        with torch.cuda.stream(slab.stream):
+            flush.zero_()
+        torch.cuda.synchronize(); barrier()
+        s.record(slab.stream)
         launches += slab.run() + 1
-        e.record()
+        e.record(slab.stream)
         torch.cuda.synchronize()
     barrier()
     wall = time.perf_counter() - wall0
