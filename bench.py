@@ -64,12 +64,12 @@ class ClockSampler:
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index: int):
-        self.rows, self.proc, self.index = [], None, index
+        self.rows, self.proc, self.index, self.t0 = [], None, index, 0.0
 
     def __enter__(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -79,7 +79,11 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+            self.rows.append([time.perf_counter()] + [x.strip() for x in line.split(",")])
+
+    def mark(self):
+        """Start of the window whose samples are reported (samples before it are dropped)."""
+        self.t0 = time.perf_counter()
 
     def __exit__(self, *exc):
         if self.proc:
@@ -93,6 +97,9 @@ class ClockSampler:
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for r in self.rows:
+            if r[0] < self.t0:
+                continue
+            r = r[1:]
             try:
                 sm.append(float(r[0])); mx.append(float(r[1]))
             except Exception:
@@ -195,24 +202,25 @@ def run_ours(args, rank, local_rank, world):
         if world > 1:
             dist.barrier()
 
-    with torch.cuda.stream(stream):
+    with torch.cuda.stream(stream), ClockSampler(local_rank) as clocks:
         for _ in range(args.warmup):
             solver.solve_device(); solver.sync()
         ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
         iter_ms, prep_ms, launches = [], [], 0
         barrier(); torch.cuda.synchronize()
-        with ClockSampler(local_rank) as clocks:
-            wall0 = time.perf_counter()
-            for s, e in ev:
-                flush.zero_()                      # cold L2 at the start of every step
-                s.record(stream)
-                solver.solve_device()
-                e.record(stream)
-                solver.sync()
-                t = solver.timing()
-                iter_ms.append(t.iterate_ms); prep_ms.append(t.prepare_ms); launches += t.launches
-            torch.cuda.synchronize(); barrier()
-            wall = time.perf_counter() - wall0
+        clocks.mark()
+        wall0 = time.perf_counter()
+        for s, e in ev:
+            flush.zero_()                      # cold L2 at the start of every step
+            s.record(stream)
+            solver.solve_device()
+            e.record(stream)
+            solver.sync()
+            t = solver.timing()
+            iter_ms.append(t.iterate_ms); prep_ms.append(t.prepare_ms); launches += t.launches
+        torch.cuda.synchronize(); barrier()
+        wall = time.perf_counter() - wall0
+        time.sleep(0.05)                       # let the last nvidia-smi sample of the window arrive
         step_ms = [s.elapsed_time(e) for s, e in ev]
     tm = solver.timing()
     total_ms = torch.tensor([sum(step_ms)], dtype=torch.float64, device=dev)
@@ -304,7 +312,7 @@ def run_ours(args, rank, local_rank, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="1080p", choices=sorted(WORKLOADS))

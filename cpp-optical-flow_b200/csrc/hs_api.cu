@@ -66,6 +66,7 @@ struct hs_ctx {
     CUtensorMap tm_u[2], tm_v[2], tm_cpk, tm_inv;
     int kernel_id = 0;  // 0 generic, 1 fused tile
     int num_sms = 148;
+    bool use_pdl = true;
     int k = 1;
 
     cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -155,10 +156,18 @@ struct Tile {
         tg.ntiles = tg.tiles_x * tg.tiles_y * c->B;
         const int grid = std::min(tg.ntiles, c->num_sms);      // persistent: one CTA per SM
         const float kf = 1.0f / (float)(c->w * c->w);
-        kernel()<<<grid, TS::THREADS, TS::SMEM, c->stream>>>(
-            c->tm_u[c->cur], c->tm_v[c->cur], c->tm_cpk, c->tm_inv, c->d_u[c->cur ^ 1],
-            c->d_v[c->cur ^ 1], c->geom(), tg, kf);
-        return cudaGetLastError();
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(grid);
+        cfg.blockDim = dim3(TS::THREADS);
+        cfg.dynamicSmemBytes = TS::SMEM;
+        cfg.stream = c->stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;   // PDL: see pdl_wait() in the kernel
+        attr[0].val.programmaticStreamSerializationAllowed = c->use_pdl ? 1 : 0;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        return cudaLaunchKernelEx(&cfg, kernel(), c->tm_u[c->cur], c->tm_v[c->cur], c->tm_cpk, c->tm_inv,
+                                  c->d_u[c->cur ^ 1], c->d_v[c->cur ^ 1], c->geom(), tg, kf);
     }
 };
 
@@ -364,6 +373,7 @@ int hs_create(const hs_config* cfg_in, hs_ctx** out) {
     if ((e = cudaGetDeviceProperties(&prop, dev)) != cudaSuccess)
         return bail(fail(c, HS_ERR_CUDA, "cudaGetDeviceProperties: %s", cudaGetErrorString(e)));
     c->num_sms = prop.multiProcessorCount;
+    c->use_pdl = env_int("HS_NO_PDL", 0) == 0;
     if (prop.major < 10)
         return bail(fail(c, HS_ERR_UNSUPPORTED, "device %d is sm_%d%d; this library is built for sm_100a (B200) only",
                          dev, prop.major, prop.minor));

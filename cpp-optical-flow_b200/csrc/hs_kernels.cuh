@@ -32,14 +32,18 @@ struct Geom {
 };
 
 // Gradient coefficients are exact small integers (|Ix|,|Iy| <= 1020, |It| <= 255), so the three of
-// them share one 32-bit word: Ix in bits 31..21, Iy in 20..10, It in 9..0 (two's complement fields).
+// them share one 32-bit word as BIASED unsigned fields: Ix+1024 in bits 31..21, Iy+1024 in 20..10,
+// It+512 in 9..0.  Unpacking is the classic magic-number conversion: OR the field into the mantissa
+// of 2^23 and subtract (2^23 + bias) - shift/LOP3/FADD on the main pipes, no I2F on the XU pipe.
+// The all-zero word TMA fills in for out-of-image pixels decodes to (-1024, -1024, -512); those
+// pixels are forced to 0 after every sweep (masked path), so the value is never used.
 __device__ __forceinline__ uint32_t pack_coef(int gx, int gy, int gt) {
-    return ((uint32_t)(gx & 0x7ff) << 21) | ((uint32_t)(gy & 0x7ff) << 10) | (uint32_t)(gt & 0x3ff);
+    return ((uint32_t)(gx + 1024) << 21) | ((uint32_t)(gy + 1024) << 10) | (uint32_t)(gt + 512);
 }
 __device__ __forceinline__ void unpack_coef(uint32_t w, float& ix, float& iy, float& it) {
-    ix = (float)((int)w >> 21);
-    iy = (float)((int)(w << 11) >> 21);
-    it = (float)((int)(w << 22) >> 22);
+    ix = __fsub_rn(__uint_as_float((w >> 21) | 0x4B000000u), 8389632.0f);            // 2^23 + 1024
+    iy = __fsub_rn(__uint_as_float(((w >> 10) & 0x7ffu) | 0x4B000000u), 8389632.0f);
+    it = __fsub_rn(__uint_as_float((w & 0x3ffu) | 0x4B000000u), 8389120.0f);         // 2^23 + 512
 }
 
 __device__ __forceinline__ int reflect101(int i, int n) {
@@ -201,6 +205,16 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, u
         " [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(smem_u32(dst)),
         "l"(reinterpret_cast<uint64_t>(map)), "r"(x), "r"(y), "r"(z), "r"(smem_u32(bar))
         : "memory");
+}
+// Programmatic dependent launch: consecutive sweep launches are chained with
+// cudaLaunchAttributeProgrammaticStreamSerialization, so a CTA of launch n+1 may become resident
+// as soon as an SM drains launch n; it must not touch global memory before pdl_wait() returns
+// (= launch n complete and flushed).
+__device__ __forceinline__ void pdl_launch_dependents() {
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+__device__ __forceinline__ void pdl_wait() {
+    asm volatile("griddepcontrol.wait;" ::: "memory");
 }
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
@@ -394,8 +408,10 @@ k_jacobi_tile(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ 
         mbar_init(&bar[0], 1);
         mbar_init(&bar[1], 1);
         fence_mbar_init();
-        if ((int)blockIdx.x < tg.ntiles) issue_tile(blockIdx.x, 0);
     }
+    pdl_launch_dependents();      // the next launch may queue up behind us (it waits in pdl_wait)
+    pdl_wait();                   // previous launch (the other ping-pong buffer's writer) is complete
+    if (tid == 0 && (int)blockIdx.x < tg.ntiles) issue_tile(blockIdx.x, 0);
     __syncthreads();
 
     int it_no = 0;
@@ -415,16 +431,19 @@ k_jacobi_tile(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ 
         const int ty0 = g.oy0 + by * tg.vy - tg.hyt;
         const int gx0 = tx0 + lane * 4;
         const int gy0 = ty0 + row0;
-        // which of the patch pixels lie inside the image (bit j*4+c)
-        uint32_t inmask = 0;
-#pragma unroll
-        for (int j = 0; j < R; ++j)
-#pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                const bool in = (gy0 + j >= 0) && (gy0 + j < g.H) && (gx0 + c >= 0) && (gx0 + c < g.W);
-                inmask |= (in ? 1u : 0u) << (j * 4 + c);
-            }
         const bool tile_inside = (tx0 >= 0) && (tx0 + TS::SX <= g.W) && (ty0 >= 0) && (ty0 + TS::SY <= g.H);
+        // which of the patch pixels lie inside the image (bit j*4+c); interior tiles never look at it
+        uint32_t inmask = 0xffffffffu;
+        if (!tile_inside) {
+            inmask = 0;
+#pragma unroll
+            for (int j = 0; j < R; ++j)
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    const bool in = (gy0 + j >= 0) && (gy0 + j < g.H) && (gx0 + c >= 0) && (gx0 + c < g.W);
+                    inmask |= (in ? 1u : 0u) << (j * 4 + c);
+                }
+        }
 
         mbar_wait(&bar[stage], (it_no >> 1) & 1);
 
