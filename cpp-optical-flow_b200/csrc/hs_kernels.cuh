@@ -308,28 +308,9 @@ __device__ __forceinline__ void tile_sweeps(float (&u)[R][4], float (&v)[R][4],
                 *reinterpret_cast<float4*>(exv + o) = make_float4(hv[j][0], hv[j][1], hv[j][2], hv[j][3]);
             }
         }
-        __syncthreads();
-        // neighbour rows: the last RL rows of the patch above, the first RR rows of the patch below
-        float au[RL > 0 ? RL : 1][4], av[RL > 0 ? RL : 1][4];
-        float bu[RR > 0 ? RR : 1][4], bv[RR > 0 ? RR : 1][4];
-#pragma unroll
-        for (int i = 0; i < RL; ++i) {
-            const size_t o = ((size_t)wa * TS::NSLOT + TS::slot(R - RL + i)) * TS::SX + lane * 4;
-            const float4 q = *reinterpret_cast<const float4*>(exu + o);
-            const float4 p = *reinterpret_cast<const float4*>(exv + o);
-            au[i][0] = q.x; au[i][1] = q.y; au[i][2] = q.z; au[i][3] = q.w;
-            av[i][0] = p.x; av[i][1] = p.y; av[i][2] = p.z; av[i][3] = p.w;
-        }
-#pragma unroll
-        for (int i = 0; i < RR; ++i) {
-            const size_t o = ((size_t)wb * TS::NSLOT + TS::slot(i)) * TS::SX + lane * 4;
-            const float4 q = *reinterpret_cast<const float4*>(exu + o);
-            const float4 p = *reinterpret_cast<const float4*>(exv + o);
-            bu[i][0] = q.x; bu[i][1] = q.y; bu[i][2] = q.z; bu[i][3] = q.w;
-            bv[i][0] = p.x; bv[i][1] = p.y; bv[i][2] = p.z; bv[i][3] = p.w;
-        }
-#pragma unroll
-        for (int j = 0; j < R; ++j) {
+        // one patch row: box sum from the row sums of rows j-RL..j+RR, then the update
+        auto update_row = [&](int j, const float (&au)[RL > 0 ? RL : 1][4], const float (&av)[RL > 0 ? RL : 1][4],
+                              const float (&bu)[RR > 0 ? RR : 1][4], const float (&bv)[RR > 0 ? RR : 1][4]) {
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
                 float su = 0.f, sv = 0.f;
@@ -353,7 +334,34 @@ __device__ __forceinline__ void tile_sweeps(float (&u)[R][4], float (&v)[R][4],
                 u[j][c] = nu;
                 v[j][c] = nv;
             }
+        };
+        float au[RL > 0 ? RL : 1][4], av[RL > 0 ? RL : 1][4];
+        float bu[RR > 0 ? RR : 1][4], bv[RR > 0 ? RR : 1][4];
+        // rows whose window stays inside the patch need nothing from the neighbours: do them while
+        // the exchange rows of the other warps are still on their way
+#pragma unroll
+        for (int j = RL; j < R - RR; ++j) update_row(j, au, av, bu, bv);
+        __syncthreads();
+        // neighbour rows: the last RL rows of the patch above, the first RR rows of the patch below
+#pragma unroll
+        for (int i = 0; i < RL; ++i) {
+            const size_t o = ((size_t)wa * TS::NSLOT + TS::slot(R - RL + i)) * TS::SX + lane * 4;
+            const float4 q = *reinterpret_cast<const float4*>(exu + o);
+            const float4 p = *reinterpret_cast<const float4*>(exv + o);
+            au[i][0] = q.x; au[i][1] = q.y; au[i][2] = q.z; au[i][3] = q.w;
+            av[i][0] = p.x; av[i][1] = p.y; av[i][2] = p.z; av[i][3] = p.w;
         }
+#pragma unroll
+        for (int i = 0; i < RR; ++i) {
+            const size_t o = ((size_t)wb * TS::NSLOT + TS::slot(i)) * TS::SX + lane * 4;
+            const float4 q = *reinterpret_cast<const float4*>(exu + o);
+            const float4 p = *reinterpret_cast<const float4*>(exv + o);
+            bu[i][0] = q.x; bu[i][1] = q.y; bu[i][2] = q.z; bu[i][3] = q.w;
+            bv[i][0] = p.x; bv[i][1] = p.y; bv[i][2] = p.z; bv[i][3] = p.w;
+        }
+#pragma unroll
+        for (int j = 0; j < R; ++j)
+            if (j < RL || j >= R - RR) update_row(j, au, av, bu, bv);
     }
 }
 
@@ -385,7 +393,8 @@ k_jacobi_tile(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ 
 
     // Start coordinates are multiples of 4 floats = 16 B: UTMALDG faults ("illegal instruction")
     // on sm_100a when the innermost start offset is not 16-byte aligned (measured, tools/tma_probe.cu).
-    auto issue_tile = [&](int t, int stage) {
+    // part 1 = coefficient boxes (never written by a sweep launch), part 2 = u, v boxes
+    auto issue_tile = [&](int t, int stage, bool coef, bool flow) {
         const int b = t / per_img;
         const int r = t - b * per_img;
         const int by = r / tg.tiles_x;
@@ -393,11 +402,15 @@ k_jacobi_tile(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ 
         const int x0 = bx * tg.vx - tg.hxl;
         const int y0 = g.oy0 + by * tg.vy - tg.hyt;
         unsigned char* st = smem + (size_t)stage * TS::STAGE;
-        mbar_expect_tx(&bar[stage], TS::TX_BYTES);
-        tma_load_3d(st + TS::OFF_U, &tm_u, &bar[stage], x0, y0, b);
-        tma_load_3d(st + TS::OFF_V, &tm_v, &bar[stage], x0, y0, b);
-        tma_load_3d(st + TS::OFF_CPK, &tm_cpk, &bar[stage], x0, y0, b);
-        tma_load_3d(st + TS::OFF_INV, &tm_inv, &bar[stage], x0, y0, b);
+        if (coef) {
+            mbar_expect_tx(&bar[stage], TS::TX_BYTES);
+            tma_load_3d(st + TS::OFF_CPK, &tm_cpk, &bar[stage], x0, y0, b);
+            tma_load_3d(st + TS::OFF_INV, &tm_inv, &bar[stage], x0, y0, b);
+        }
+        if (flow) {
+            tma_load_3d(st + TS::OFF_U, &tm_u, &bar[stage], x0, y0, b);
+            tma_load_3d(st + TS::OFF_V, &tm_v, &bar[stage], x0, y0, b);
+        }
     };
 
     if (tid == 0) {
@@ -408,10 +421,12 @@ k_jacobi_tile(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ 
         mbar_init(&bar[0], 1);
         mbar_init(&bar[1], 1);
         fence_mbar_init();
+        // the first tile's coefficients can stream in while the previous launch is still draining
+        if ((int)blockIdx.x < tg.ntiles) issue_tile(blockIdx.x, 0, true, false);
     }
     pdl_launch_dependents();      // the next launch may queue up behind us (it waits in pdl_wait)
-    pdl_wait();                   // previous launch (the other ping-pong buffer's writer) is complete
-    if (tid == 0 && (int)blockIdx.x < tg.ntiles) issue_tile(blockIdx.x, 0);
+    pdl_wait();                   // previous launch (the writer of the u, v we read) is complete
+    if (tid == 0 && (int)blockIdx.x < tg.ntiles) issue_tile(blockIdx.x, 0, false, true);
     __syncthreads();
 
     int it_no = 0;
@@ -468,7 +483,7 @@ k_jacobi_tile(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ 
         fence_proxy_async();      // our generic-proxy scratch accesses of the other stage, before TMA rewrites it
         __syncthreads();
         if (tid == 0 && t + (int)gridDim.x < tg.ntiles)
-            issue_tile(t + gridDim.x, stage ^ 1);     // lands underneath this tile's k sweeps
+            issue_tile(t + gridDim.x, stage ^ 1, true, true);   // lands underneath this tile's k sweeps
 
         float* s_ex = reinterpret_cast<float*>(st);
         if (tile_inside)
