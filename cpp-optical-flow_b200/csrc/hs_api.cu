@@ -59,6 +59,9 @@ struct hs_ctx {
     float* d_v[2] = {nullptr, nullptr};
     int cur = 0;
     uint32_t* d_cpk = nullptr;   // packed {Ix, Iy, It}
+    int* d_done = nullptr;       // per-tile phase counters of a multi-phase launch
+    size_t done_cap = 0;
+    bool multi_phase = true;     // whole hs_iterate in one launch (single-GPU) vs one launch per k sweeps
     float* d_inv = nullptr;
     void* d_out = nullptr;
     size_t out_bytes = 0;
@@ -144,30 +147,57 @@ struct Tile {
         return cudaFuncSetAttribute(kernel(), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TS::SMEM);
     }
     static int max_k() { return (TS::SY - 1) / std::max(1, RL + RR); }
-    static cudaError_t launch(hs_ctx* c, int kk) {
+    // One launch advances `sweeps` sweeps in phases of k.  phases > 1 needs every CTA resident at
+    // once (they wait on each other's tiles) -> cooperative launch; a single phase is chained to
+    // the previous launch with programmatic dependent launch instead.
+    static cudaError_t launch(hs_ctx* c, int k, int sweeps) {
         hs::TileGrid tg;
-        tg.k = kk;
-        tg.hxl = round_up(RL * kk, 4);
-        tg.hyt = RL * kk;
-        tg.vx = TS::SX - tg.hxl - round_up(RR * kk, 4);
-        tg.vy = TS::SY - tg.hyt - RR * kk;
+        tg.k = k;
+        tg.sweeps = sweeps;
+        tg.hxl = round_up(RL * k, 4);
+        tg.hyt = RL * k;
+        tg.vx = TS::SX - tg.hxl - round_up(RR * k, 4);
+        tg.vy = TS::SY - tg.hyt - RR * k;
         tg.tiles_x = (c->W + tg.vx - 1) / tg.vx;
         tg.tiles_y = (c->oy1 - c->oy0 + tg.vy - 1) / tg.vy;
         tg.ntiles = tg.tiles_x * tg.tiles_y * c->B;
+        const int phases = (sweeps + k - 1) / k;
         const int grid = std::min(tg.ntiles, c->num_sms);      // persistent: one CTA per SM
         const float kf = 1.0f / (float)(c->w * c->w);
+        if (phases > 1) {
+            if ((size_t)tg.ntiles > c->done_cap) return cudaErrorInvalidValue;
+            cudaError_t e = cudaMemsetAsync(c->d_done, 0, (size_t)tg.ntiles * sizeof(int), c->stream);
+            if (e != cudaSuccess) return e;
+        }
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3(grid);
         cfg.blockDim = dim3(TS::THREADS);
         cfg.dynamicSmemBytes = TS::SMEM;
         cfg.stream = c->stream;
         cudaLaunchAttribute attr[1];
-        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;   // PDL: see pdl_wait() in the kernel
-        attr[0].val.programmaticStreamSerializationAllowed = c->use_pdl ? 1 : 0;
+        if (phases > 1) {
+            attr[0].id = cudaLaunchAttributeCooperative;
+            attr[0].val.cooperative = 1;
+        } else {
+            attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;   // PDL: see pdl_wait() in the kernel
+            attr[0].val.programmaticStreamSerializationAllowed = c->use_pdl ? 1 : 0;
+        }
         cfg.attrs = attr;
         cfg.numAttrs = 1;
-        return cudaLaunchKernelEx(&cfg, kernel(), c->tm_u[c->cur], c->tm_v[c->cur], c->tm_cpk, c->tm_inv,
-                                  c->d_u[c->cur ^ 1], c->d_v[c->cur ^ 1], c->geom(), tg, kf);
+        const int a = c->cur, b = c->cur ^ 1;
+        return cudaLaunchKernelEx(&cfg, kernel(), c->tm_u[a], c->tm_v[a], c->tm_u[b], c->tm_v[b], c->tm_cpk,
+                                  c->tm_inv, c->d_u[a], c->d_v[a], c->d_u[b], c->d_v[b], c->d_done, c->geom(),
+                                  tg, kf);
+    }
+    static size_t max_tiles(const hs_ctx* c) {                 // upper bound over all k (k = 1 tiles are the largest)
+        size_t best = 0;
+        for (int k = 1; k <= max_k(); ++k) {
+            const int vx = TS::SX - round_up(RL * k, 4) - round_up(RR * k, 4), vy = TS::SY - (RL + RR) * k;
+            if (vx <= 0 || vy <= 0) break;
+            const size_t n = (size_t)((c->W + vx - 1) / vx) * ((c->oy1 - c->oy0 + vy - 1) / vy) * c->B;
+            best = std::max(best, n);
+        }
+        return best;
     }
 };
 
@@ -240,11 +270,14 @@ int do_iterate(hs_ctx* c, int iters) {
     if (iters < 0) return fail(c, HS_ERR_INVALID_ARG, "negative iteration count");
     int left = iters;
     while (left > 0) {
-        int kk = 1;
+        int step = 1;
         cudaError_t e = cudaSuccess;
         if (c->kernel_id == 1) {
-            kk = std::min(c->k, left);
-            tile_dispatch(c->RL, c->RR, [&](auto t) { e = decltype(t)::launch(c, kk); });
+            // everything in one multi-phase launch, unless the caller must refresh halos between
+            // fused launches (row slabs) or asked for per-launch behaviour
+            step = c->multi_phase ? left : std::min(c->k, left);
+            tile_dispatch(c->RL, c->RR, [&](auto t) { e = decltype(t)::launch(c, std::min(c->k, step), step); });
+            if (e == cudaSuccess && (((step + c->k - 1) / c->k) & 1)) c->cur ^= 1;
         } else {
             dim3 block(32, 8);
             dim3 grid((c->W + 31) / 32, (c->oy1 - c->oy0 + 7) / 8, c->B);
@@ -253,10 +286,10 @@ int do_iterate(hs_ctx* c, int iters) {
                                                                 c->d_v[c->cur ^ 1], c->d_cpk, c->d_inv,
                                                                 c->geom(), c->w, c->a, kf);
             e = cudaGetLastError();
+            c->cur ^= 1;
         }
         if (e != cudaSuccess) return fail(c, HS_ERR_CUDA, "sweep launch failed: %s", cudaGetErrorString(e));
-        c->cur ^= 1;
-        left -= kk;
+        left -= step;
         c->timing.launches += 1;
     }
     return HS_OK;
@@ -303,7 +336,7 @@ void destroy_impl(hs_ctx* c) {
         if (c->stream) cudaStreamSynchronize(c->stream);
         cudaFree(c->d_prev); cudaFree(c->d_next);
         for (int i = 0; i < 2; ++i) { cudaFree(c->d_u[i]); cudaFree(c->d_v[i]); }
-        cudaFree(c->d_cpk); cudaFree(c->d_inv); cudaFree(c->d_out);
+        cudaFree(c->d_cpk); cudaFree(c->d_inv); cudaFree(c->d_done); cudaFree(c->d_out);
         for (auto& e : c->ev) if (e) cudaEventDestroy(e);
         if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
     }
@@ -441,6 +474,16 @@ int hs_create(const hs_config* cfg_in, hs_ctx** out) {
         return bail(fail(c, HS_ERR_INVALID_ARG,
                          "row slab needs %d halo rows above and %d below its output rows for k=%d (have %d / %d)",
                          c->RL * c->k, c->RR * c->k, c->k, c->oy0, c->H - c->oy1));
+    if (c->kernel_id == 1) {
+        size_t cap = 0;
+        tile_dispatch(c->RL, c->RR, [&](auto t) { cap = decltype(t)::max_tiles(c); });
+        HS_CREATE_CUDA(cudaMalloc(&c->d_done, std::max<size_t>(cap, 1) * sizeof(int)));
+        c->done_cap = cap;
+        int coop = 0;
+        cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
+        c->multi_phase = coop && !c->top_seam && !c->bot_seam && !(cfg.flags & HS_FLAG_SINGLE_PHASE) &&
+                         env_int("HS_SINGLE_PHASE", 0) == 0;
+    }
     c->timing.temporal_k = c->k;
     c->timing.kernel_id = c->kernel_id;
     *out = c;

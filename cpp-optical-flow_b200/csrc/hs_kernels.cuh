@@ -182,8 +182,39 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
                  "r"(bytes)
                  : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {   // non-blocking
+    uint32_t done;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(done)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return done != 0;
+}
+// barrier among the compute warps only (the producer warp never joins it)
+template <int THREADS>
+__device__ __forceinline__ void compute_sync() {
+    asm volatile("bar.sync 1, %0;" ::"n"(THREADS) : "memory");
+}
+__device__ __forceinline__ unsigned long long global_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+// Every device-side wait is bounded: a protocol bug must end in a trapped kernel, never in a GPU
+// that spins forever (a hung kernel cannot be killed from the host).
+constexpr unsigned long long WAIT_LIMIT_NS = 4000000000ull;   // 4 s
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     uint32_t done;
+    unsigned long long t0 = 0;
+    uint32_t spins = 0;
     do {
         asm volatile(
             "{\n"
@@ -194,6 +225,11 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
             : "=r"(done)
             : "r"(smem_u32(bar)), "r"(parity)
             : "memory");
+        if (!done && (++spins & 0x3ff) == 0) {
+            const unsigned long long now = global_ns();
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > WAIT_LIMIT_NS) __trap();
+        }
     } while (!done);
 }
 // 3-D tiled load: coordinates (x, y, pair), innermost first; out-of-bounds elements read as 0,
@@ -243,7 +279,9 @@ struct TileShape {
     static_assert(RL <= R && RR <= R, "a thread's vertical neighbours are the adjacent patches only");
     static constexpr int SX = 128;
     static constexpr int SY = NWARP * R;
-    static constexpr int THREADS = NWARP * 32;
+    static constexpr int CTHREADS = NWARP * 32;      // compute threads
+    static constexpr int THREADS = CTHREADS + 128;   // + one producer warp group (setmaxnreg works per 4 warps;
+                                                     //   only its first warp does anything)
     static constexpr int NSLOT = (RL + RR < R) ? (RL + RR) : R;       // patch rows a neighbour reads
     static constexpr size_t BYTES_F32 = (size_t)SX * SY * 4;
     static constexpr size_t OFF_U = 0;                                // offsets inside one stage
@@ -256,7 +294,7 @@ struct TileShape {
     static constexpr size_t BYTES_EX = 2 * 2 * EX_FIELD * 4;
     static_assert(BYTES_EX <= STAGE, "exchange array must fit in one stage");
     static constexpr size_t OFF_BAR = 2 * STAGE;
-    static constexpr size_t SMEM = OFF_BAR + 16;
+    static constexpr size_t SMEM = OFF_BAR + 64;                      // full[2], empty[2], stored[2]
     static constexpr uint32_t TX_BYTES = (uint32_t)STAGE;
     // slot of patch row j in the exchange array (-1: no neighbour reads it)
     __host__ __device__ static constexpr int slot(int j) {
@@ -341,7 +379,7 @@ __device__ __forceinline__ void tile_sweeps(float (&u)[R][4], float (&v)[R][4],
         // the exchange rows of the other warps are still on their way
 #pragma unroll
         for (int j = RL; j < R - RR; ++j) update_row(j, au, av, bu, bv);
-        __syncthreads();
+        compute_sync<TS::CTHREADS>();
         // neighbour rows: the last RL rows of the patch above, the first RR rows of the patch below
 #pragma unroll
         for (int i = 0; i < RL; ++i) {
@@ -367,83 +405,186 @@ __device__ __forceinline__ void tile_sweeps(float (&u)[R][4], float (&v)[R][4],
 
 // geometry of one launch (host-computed, same for every tile)
 struct TileGrid {
-    int k;                 // sweeps fused in this launch
+    int k;                 // sweeps fused per phase (tile geometry is sized for this)
+    int sweeps;            // total sweeps of this launch = phases * k (the last phase may be short)
     int hxl, hyt;          // halo columns left / rows above the stored centre
     int vx, vy;            // stored centre of a tile
     int tiles_x, tiles_y;  // tiles per image
     int ntiles;            // tiles_x * tiles_y * batch
 };
 
+// gpu-scope flag helpers for the inter-CTA dataflow of a multi-phase launch
+__device__ __forceinline__ int ld_relaxed_gpu(const int* p) {
+    int v;
+    asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_gpu(int* p, int v) {
+    asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void fence_acq_rel_gpu() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+
+// One launch = `phases` phases of up to k sweeps over every tile.  Phase p reads the flow planes
+// (p & 1) and writes the planes ((p & 1) ^ 1).  There is NO grid-wide barrier between phases:
+// tile t may start phase p as soon as t and its 8 neighbours have finished phase p-1 (their
+// per-tile counters `done[]` say so), which covers both the read-after-write on the halo and the
+// write-after-read on the plane that is overwritten.  Each CTA owns the same tiles in every phase
+// (static round robin), so by the time it wraps around to its first tile the neighbours' results
+// are long there and the TMA prefetch of the next tile keeps overlapping the current one.
+// All CTAs must be co-resident (grid <= #SMs, cooperative launch) because they wait on one another.
+//
+// Warp roles: warps 0..NWARP-1 compute; warp NWARP is the producer.  The producer owns everything
+// with long latency that is not arithmetic: it polls the neighbours' counters, fences, issues the
+// TMA boxes of the next item into the free stage (empty[] -> full[] mbarriers) and publishes this
+// CTA's finished tiles (stored[] mbarrier -> fence -> counter), polling all of that without ever
+// blocking on one duty, so a CTA can never hold back a tile somebody else is waiting for.
 template <int RL, int RR, int R, int NWARP>
-__global__ void __launch_bounds__(NWARP * 32, 1)
-k_jacobi_tile(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CUtensorMap tm_v,
+__global__ void __launch_bounds__(NWARP * 32 + 128, 1)
+k_jacobi_tile(const __grid_constant__ CUtensorMap tm_u0, const __grid_constant__ CUtensorMap tm_v0,
+              const __grid_constant__ CUtensorMap tm_u1, const __grid_constant__ CUtensorMap tm_v1,
               const __grid_constant__ CUtensorMap tm_cpk, const __grid_constant__ CUtensorMap tm_inv,
-              float* __restrict__ un, float* __restrict__ vn, Geom g, TileGrid tg, float kf) {
+              float* __restrict__ u0, float* __restrict__ v0, float* __restrict__ u1, float* __restrict__ v1,
+              int* __restrict__ done, Geom g, TileGrid tg, float kf) {
     using TS = TileShape<RL, RR, R, NWARP>;
     static_assert(R * 4 <= 32, "in-image mask is one 32-bit word per thread");
     static_assert(RL <= 4 && RR <= 4, "horizontal neighbours come from the adjacent lane only");
+    static_assert(NWARP % 4 == 0, "setmaxnreg acts on whole warp groups");
     extern __shared__ __align__(128) unsigned char smem[];
-    uint64_t* bar = reinterpret_cast<uint64_t*>(smem + TS::OFF_BAR);   // full[2]
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + TS::OFF_BAR);  // TMA bytes landed      [2]
+    uint64_t* empty = full + 2;                                        // stage may be refilled [2]
+    uint64_t* stored = full + 4;                                       // tile results stored   [2]
 
     const int tid = threadIdx.x;
     const int lane = tid & 31;
     const int warp = tid >> 5;
-    const int row0 = warp * R;                        // first tile row of this thread's patch
     const int per_img = tg.tiles_x * tg.tiles_y;
+    const int G = gridDim.x;
+    const int my_tiles = (tg.ntiles - (int)blockIdx.x + G - 1) / G;     // >= 1 (grid <= ntiles)
+    const int phases = (tg.sweeps + tg.k - 1) / tg.k;
+    const int items = phases * my_tiles;              // work items of this CTA, phase-major
 
-    // Start coordinates are multiples of 4 floats = 16 B: UTMALDG faults ("illegal instruction")
-    // on sm_100a when the innermost start offset is not 16-byte aligned (measured, tools/tma_probe.cu).
-    // part 1 = coefficient boxes (never written by a sweep launch), part 2 = u, v boxes
-    auto issue_tile = [&](int t, int stage, bool coef, bool flow) {
-        const int b = t / per_img;
-        const int r = t - b * per_img;
-        const int by = r / tg.tiles_x;
-        const int bx = r - by * tg.tiles_x;
-        const int x0 = bx * tg.vx - tg.hxl;
-        const int y0 = g.oy0 + by * tg.vy - tg.hyt;
-        unsigned char* st = smem + (size_t)stage * TS::STAGE;
-        if (coef) {
-            mbar_expect_tx(&bar[stage], TS::TX_BYTES);
-            tma_load_3d(st + TS::OFF_CPK, &tm_cpk, &bar[stage], x0, y0, b);
-            tma_load_3d(st + TS::OFF_INV, &tm_inv, &bar[stage], x0, y0, b);
-        }
-        if (flow) {
-            tma_load_3d(st + TS::OFF_U, &tm_u, &bar[stage], x0, y0, b);
-            tma_load_3d(st + TS::OFF_V, &tm_v, &bar[stage], x0, y0, b);
-        }
+    struct Item { int p, t, b, bx, by, x0, y0; };
+    auto item_of = [&](int n) {
+        Item it;
+        it.p = n / my_tiles;
+        it.t = blockIdx.x + (n - it.p * my_tiles) * G;
+        it.b = it.t / per_img;
+        const int r = it.t - it.b * per_img;
+        it.by = r / tg.tiles_x;
+        it.bx = r - it.by * tg.tiles_x;
+        it.x0 = it.bx * tg.vx - tg.hxl;               // staged tile origin (may be negative)
+        it.y0 = g.oy0 + it.by * tg.vy - tg.hyt;
+        return it;
     };
 
     if (tid == 0) {
-        tma_prefetch_desc(&tm_u);
-        tma_prefetch_desc(&tm_v);
-        tma_prefetch_desc(&tm_cpk);
-        tma_prefetch_desc(&tm_inv);
-        mbar_init(&bar[0], 1);
-        mbar_init(&bar[1], 1);
+        mbar_init(&full[0], 1);
+        mbar_init(&full[1], 1);
+        mbar_init(&empty[0], 1);
+        mbar_init(&empty[1], 1);
+        mbar_init(&stored[0], NWARP);
+        mbar_init(&stored[1], NWARP);
         fence_mbar_init();
-        // the first tile's coefficients can stream in while the previous launch is still draining
-        if ((int)blockIdx.x < tg.ntiles) issue_tile(blockIdx.x, 0, true, false);
     }
-    pdl_launch_dependents();      // the next launch may queue up behind us (it waits in pdl_wait)
-    pdl_wait();                   // previous launch (the writer of the u, v we read) is complete
-    if (tid == 0 && (int)blockIdx.x < tg.ntiles) issue_tile(blockIdx.x, 0, false, true);
     __syncthreads();
 
-    int it_no = 0;
-    for (int t = blockIdx.x; t < tg.ntiles; t += gridDim.x, ++it_no) {
-        const int stage = it_no & 1;
+    // 512 threads are launched with 128 registers each (the whole register file).  The producer warp
+    // group hands most of its share back and the three compute warp groups take it.
+    if (warp >= NWARP) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+        if (warp > NWARP) return;
+        // ================================ producer warp ================================
+        // Start coordinates are multiples of 4 floats = 16 B: UTMALDG faults ("illegal instruction")
+        // on sm_100a when the innermost start offset is not 16-byte aligned (tools/tma_probe.cu).
+        auto issue = [&](const Item& it, int stage, bool coef, bool flow) {   // lane 0 only
+            unsigned char* st = smem + (size_t)stage * TS::STAGE;
+            if (coef) {   // coefficient boxes are never written by a sweep launch
+                mbar_expect_tx(&full[stage], TS::TX_BYTES);
+                tma_load_3d(st + TS::OFF_CPK, &tm_cpk, &full[stage], it.x0, it.y0, it.b);
+                tma_load_3d(st + TS::OFF_INV, &tm_inv, &full[stage], it.x0, it.y0, it.b);
+            }
+            if (flow) {
+                tma_load_3d(st + TS::OFF_U, (it.p & 1) ? &tm_u1 : &tm_u0, &full[stage], it.x0, it.y0, it.b);
+                tma_load_3d(st + TS::OFF_V, (it.p & 1) ? &tm_v1 : &tm_v0, &full[stage], it.x0, it.y0, it.b);
+            }
+        };
+        if (lane == 0) {
+            tma_prefetch_desc(&tm_u0);
+            tma_prefetch_desc(&tm_v0);
+            tma_prefetch_desc(&tm_u1);
+            tma_prefetch_desc(&tm_v1);
+            tma_prefetch_desc(&tm_cpk);
+            tma_prefetch_desc(&tm_inv);
+        }
+        pdl_launch_dependents();      // the next launch may queue up behind us (it waits in pdl_wait)
+        pdl_wait();                   // whatever wrote the planes we read (K1, a sweep launch, a halo copy) is done
+        if (lane == 0) issue(item_of(0), 0, true, true);
+
+        int mi = 1;                   // next item to issue
+        int np = 0;                   // next item to publish (multi-phase launches only)
+        const bool publish = phases > 1;
+        unsigned long long t_idle = 0;
+        uint32_t idle = 0;
+        while (mi < items || (publish && np < items)) {
+            bool progress = false;
+            if (publish && np < items && mbar_test(&stored[np & 1], (np >> 1) & 1)) {
+                // all compute warps have stored item np (their arrive is ordered after their stores);
+                // make those stores visible GPU-wide, then bump the tile's counter
+                if (lane == 0) {
+                    const Item it = item_of(np);
+                    fence_acq_rel_gpu();
+                    st_release_gpu(done + it.t, it.p + 1);
+                }
+                ++np;
+                progress = true;
+            }
+            if (mi < items && (mi < 2 || mbar_test(&empty[mi & 1], ((mi - 2) >> 1) & 1))) {
+                const Item nx = item_of(mi);
+                int dep = 0x7fffffff;                 // lanes 0..8: one neighbour counter each
+                if (nx.p > 0 && lane < 9) {
+                    const int yy = nx.by + lane / 3 - 1, xx = nx.bx + lane % 3 - 1;
+                    if (yy >= 0 && yy < tg.tiles_y && xx >= 0 && xx < tg.tiles_x)
+                        dep = ld_relaxed_gpu(done + nx.b * per_img + yy * tg.tiles_x + xx);
+                }
+                const int m = __reduce_min_sync(0xffffffffu, dep);
+                if (m >= nx.p) {      // this tile and its neighbours have finished phase p-1
+                    if (lane == 0) {
+                        fence_acq_rel_gpu();          // acquire: their stores are visible ...
+                        fence_proxy_async_all();      // ... also to the async proxy (TMA) reads
+                        issue(nx, mi & 1, true, true);
+                    }
+                    ++mi;
+                    progress = true;
+                }
+            }
+            if (!progress) {
+                __nanosleep(32);
+                if ((++idle & 0x3ff) == 0) {
+                    const unsigned long long now = global_ns();
+                    if (t_idle == 0) t_idle = now;
+                    else if (now - t_idle > WAIT_LIMIT_NS) __trap();
+                }
+            } else {
+                t_idle = 0;
+            }
+        }
+        return;
+    }
+
+    // ================================ compute warps ================================
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 152;");
+    const int row0 = warp * R;                        // first tile row of this thread's patch
+    for (int n = 0; n < items; ++n) {
+        const Item cur = item_of(n);
+        const int stage = n & 1;
         unsigned char* st = smem + (size_t)stage * TS::STAGE;
         const float* s_u = reinterpret_cast<const float*>(st + TS::OFF_U);
         const float* s_v = reinterpret_cast<const float*>(st + TS::OFF_V);
         const uint32_t* s_cpk = reinterpret_cast<const uint32_t*>(st + TS::OFF_CPK);
         const float* s_inv = reinterpret_cast<const float*>(st + TS::OFF_INV);
 
-        const int b = t / per_img;
-        const int r = t - b * per_img;
-        const int by = r / tg.tiles_x;
-        const int bx = r - by * tg.tiles_x;
-        const int tx0 = bx * tg.vx - tg.hxl;          // staged tile origin (may be negative)
-        const int ty0 = g.oy0 + by * tg.vy - tg.hyt;
+        const int tx0 = cur.x0, ty0 = cur.y0, b = cur.b;
         const int gx0 = tx0 + lane * 4;
         const int gy0 = ty0 + row0;
         const bool tile_inside = (tx0 >= 0) && (tx0 + TS::SX <= g.W) && (ty0 >= 0) && (ty0 + TS::SY <= g.H);
@@ -460,7 +601,7 @@ k_jacobi_tile(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ 
                 }
         }
 
-        mbar_wait(&bar[stage], (it_no >> 1) & 1);
+        mbar_wait(&full[stage], (n >> 1) & 1);
 
         float u[R][4], v[R][4], ix[R][4], iy[R][4], it[R][4], iv[R][4];
 #pragma unroll
@@ -481,21 +622,21 @@ k_jacobi_tile(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ 
         // Everyone has (a) finished the previous tile - its exchange scratch in the OTHER stage is
         // dead - and (b) pulled this tile out of THIS stage, which now becomes the exchange scratch.
         fence_proxy_async();      // our generic-proxy scratch accesses of the other stage, before TMA rewrites it
-        __syncthreads();
-        if (tid == 0 && t + (int)gridDim.x < tg.ntiles)
-            issue_tile(t + gridDim.x, stage ^ 1, true, true);   // lands underneath this tile's k sweeps
+        compute_sync<TS::CTHREADS>();
+        if (tid == 0 && n >= 1) mbar_arrive(&empty[stage ^ 1]);   // producer may refill it with item n+1
 
         float* s_ex = reinterpret_cast<float*>(st);
+        const int kk = min(tg.k, tg.sweeps - cur.p * tg.k);
         if (tile_inside)
-            tile_sweeps<RL, RR, R, NWARP, false>(u, v, ix, iy, it, iv, s_ex, tg.k, kf, warp, lane, inmask);
+            tile_sweeps<RL, RR, R, NWARP, false>(u, v, ix, iy, it, iv, s_ex, kk, kf, warp, lane, inmask);
         else
-            tile_sweeps<RL, RR, R, NWARP, true>(u, v, ix, iy, it, iv, s_ex, tg.k, kf, warp, lane, inmask);
+            tile_sweeps<RL, RR, R, NWARP, true>(u, v, ix, iy, it, iv, s_ex, kk, kf, warp, lane, inmask);
 
-        // store the exact centre of the tile
+        // store the exact centre of the tile into the other pair of planes
         const int lx = lane * 4;
         if (lx >= tg.hxl && lx < tg.hxl + tg.vx && gx0 < g.W) {
-            float* U = un + (size_t)b * g.plane;
-            float* V = vn + (size_t)b * g.plane;
+            float* U = ((cur.p & 1) ? u0 : u1) + (size_t)b * g.plane;
+            float* V = ((cur.p & 1) ? v0 : v1) + (size_t)b * g.plane;
 #pragma unroll
             for (int j = 0; j < R; ++j) {
                 const int ly = row0 + j;
@@ -506,6 +647,10 @@ k_jacobi_tile(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ 
                     *reinterpret_cast<float4*>(V + o) = make_float4(v[j][0], v[j][1], v[j][2], v[j][3]);
                 }
             }
+        }
+        if (phases > 1) {             // tell the producer this warp's share of the tile is stored
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&stored[stage]);
         }
     }
 }

@@ -57,7 +57,7 @@ typedef enum hs_dtype { HS_F32 = 0, HS_F64 = 1 } hs_dtype;
 #define HS_FLAG_TOP_IS_SEAM 0x1    /* row-slab: rows exist above this context's buffer          */
 #define HS_FLAG_BOTTOM_IS_SEAM 0x2 /* row-slab: rows exist below this context's buffer          */
 #define HS_FLAG_FORCE_GENERIC 0x4  /* always use the one-sweep-per-launch kernel (A/B testing)  */
-#define HS_FLAG_NO_GRAPH 0x8       /* do not capture the sweep loop into a CUDA graph           */
+#define HS_FLAG_SINGLE_PHASE 0x8   /* one launch per k fused sweeps (no multi-phase dataflow launch) */
 
 /*
  * Replaces the three public fields + constructor of class hornSchunck (hornSchunck.cpp:10-17)
