@@ -626,6 +626,18 @@ int hs_get_timing(const hs_ctx* c, hs_timing* o) {
     return HS_OK;
 }
 
+#ifdef HS_TILE_PROFILE
+// debug build only: read (and clear) the per-CTA tile phase counters
+int hs_debug_tile_profile(long long* out, int clear) {
+    cudaError_t e = cudaMemcpyFromSymbol(out, hs::g_tile_prof, sizeof(long long) * 256 * 8);
+    if (e == cudaSuccess && clear) {
+        static long long zeros[256 * 8];
+        e = cudaMemcpyToSymbol(hs::g_tile_prof, zeros, sizeof zeros);
+    }
+    return e == cudaSuccess ? HS_OK : HS_ERR_CUDA;
+}
+#endif
+
 int hs_host_alloc(void** ptr, size_t bytes) {
     if (!ptr) return HS_ERR_INVALID_ARG;
     *ptr = nullptr;

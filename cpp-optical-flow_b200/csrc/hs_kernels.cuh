@@ -403,6 +403,18 @@ __device__ __forceinline__ void tile_sweeps(float (&u)[R][4], float (&v)[R][4],
     }
 }
 
+#ifdef HS_TILE_PROFILE
+// Debug build only (tools/tile_profile.py): per-CTA cycle counts, summed over the tiles of a launch:
+// [0] wait for TMA, [1] smem->registers + unpack + barrier, [2] sweeps, [3] stores, [4] tiles,
+// [5] TMA issue -> landed (sum), [6] (max), [7] consumer barrier -> TMA issue of the next tile.
+__device__ long long g_tile_prof[256][8];
+#define HS_PROF_T(var) const long long var = clock64()
+#define HS_PROF_ADD(slot, a, b) if (tid == 0) g_tile_prof[blockIdx.x][slot] += (b) - (a)
+#else
+#define HS_PROF_T(var)
+#define HS_PROF_ADD(slot, a, b)
+#endif
+
 // geometry of one launch (host-computed, same for every tile)
 struct TileGrid {
     int k;                 // sweeps fused per phase (tile geometry is sized for this)
@@ -429,9 +441,10 @@ __device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.pr
 // (p & 1) and writes the planes ((p & 1) ^ 1).  There is NO grid-wide barrier between phases:
 // tile t may start phase p as soon as t and its 8 neighbours have finished phase p-1 (their
 // per-tile counters `done[]` say so), which covers both the read-after-write on the halo and the
-// write-after-read on the plane that is overwritten.  Each CTA owns the same tiles in every phase
-// (static round robin), so by the time it wraps around to its first tile the neighbours' results
-// are long there and the TMA prefetch of the next tile keeps overlapping the current one.
+// write-after-read on the plane that is overwritten.  Work is one phase-major stream of
+// (phase, tile) items dealt round robin to the CTAs, so a tile's inputs were finished about one
+// whole phase (ntiles / #CTAs rounds) before its turn and the TMA prefetch of the next tile
+// keeps overlapping the current one.
 // All CTAs must be co-resident (grid <= #SMs, cooperative launch) because they wait on one another.
 //
 // Warp roles: warps 0..NWARP-1 compute; warp NWARP is the producer.  The producer owns everything
@@ -460,15 +473,20 @@ k_jacobi_tile(const __grid_constant__ CUtensorMap tm_u0, const __grid_constant__
     const int warp = tid >> 5;
     const int per_img = tg.tiles_x * tg.tiles_y;
     const int G = gridDim.x;
-    const int my_tiles = (tg.ntiles - (int)blockIdx.x + G - 1) / G;     // >= 1 (grid <= ntiles)
     const int phases = (tg.sweeps + tg.k - 1) / tg.k;
-    const int items = phases * my_tiles;              // work items of this CTA, phase-major
+    const int total = phases * tg.ntiles;             // work items of the launch, phase-major: g = p*ntiles + t
+    const int items = (total - (int)blockIdx.x + G - 1) / G;   // ... of this CTA (>= 1: grid <= ntiles)
 
+    // CTA c takes items c, c+G, c+2G, ... of the global phase-major stream.  Unless G divides the
+    // tile count this rotates the tile -> CTA assignment from phase to phase, so the slower border
+    // tiles (masked path) are shared by everybody instead of pinning a few CTAs that all their
+    // neighbours then have to wait for.
     struct Item { int p, t, b, bx, by, x0, y0; };
     auto item_of = [&](int n) {
+        const int gi = blockIdx.x + n * G;
         Item it;
-        it.p = n / my_tiles;
-        it.t = blockIdx.x + (n - it.p * my_tiles) * G;
+        it.p = gi / tg.ntiles;
+        it.t = gi - it.p * tg.ntiles;
         it.b = it.t / per_img;
         const int r = it.t - it.b * per_img;
         it.by = r / tg.tiles_x;
@@ -521,54 +539,86 @@ k_jacobi_tile(const __grid_constant__ CUtensorMap tm_u0, const __grid_constant__
         pdl_wait();                   // whatever wrote the planes we read (K1, a sweep launch, a halo copy) is done
         if (lane == 0) issue(item_of(0), 0, true, true);
 
-        int mi = 1;                   // next item to issue
-        int np = 0;                   // next item to publish (multi-phase launches only)
+        // The events the producer reacts to alternate strictly in time: "item m-2 stored" -> publish
+        // it;  "stage free" (the compute warps passed the barrier of item m-1) -> issue item m.
+        // Both are mbarrier waits that hardware-suspend the warp, so it reacts within ~100 cycles
+        // and steals no issue slots.  The only polling loop is the wait for the neighbours'
+        // counters; it keeps publishing meanwhile, so this CTA never sits on a finished tile that
+        // somebody else is waiting for (no cycle in the wait graph: dependencies always point to
+        // items that are earlier in every CTA's order).
         const bool publish = phases > 1;
-        unsigned long long t_idle = 0;
-        uint32_t idle = 0;
-        while (mi < items || (publish && np < items)) {
-            bool progress = false;
-            if (publish && np < items && mbar_test(&stored[np & 1], (np >> 1) & 1)) {
-                // all compute warps have stored item np (their arrive is ordered after their stores);
-                // make those stores visible GPU-wide, then bump the tile's counter
-                if (lane == 0) {
-                    const Item it = item_of(np);
-                    fence_acq_rel_gpu();
-                    st_release_gpu(done + it.t, it.p + 1);
-                }
-                ++np;
-                progress = true;
+        int np = 0;                   // next item to publish
+        auto do_publish = [&](int n) {
+            // all compute warps have stored item n (their arrive is ordered after their stores);
+            // make those stores visible GPU-wide, then bump the tile's counter
+            if (lane == 0) {
+                const Item it = item_of(n);
+                fence_acq_rel_gpu();
+                st_release_gpu(done + it.t, it.p + 1);
             }
-            if (mi < items && (mi < 2 || mbar_test(&empty[mi & 1], ((mi - 2) >> 1) & 1))) {
-                const Item nx = item_of(mi);
-                int dep = 0x7fffffff;                 // lanes 0..8: one neighbour counter each
-                if (nx.p > 0 && lane < 9) {
-                    const int yy = nx.by + lane / 3 - 1, xx = nx.bx + lane % 3 - 1;
-                    if (yy >= 0 && yy < tg.tiles_y && xx >= 0 && xx < tg.tiles_x)
-                        dep = ld_relaxed_gpu(done + nx.b * per_img + yy * tg.tiles_x + xx);
-                }
-                const int m = __reduce_min_sync(0xffffffffu, dep);
-                if (m >= nx.p) {      // this tile and its neighbours have finished phase p-1
-                    if (lane == 0) {
-                        fence_acq_rel_gpu();          // acquire: their stores are visible ...
-                        fence_proxy_async_all();      // ... also to the async proxy (TMA) reads
-                        issue(nx, mi & 1, true, true);
+        };
+        for (int mi = 1; mi < items; ++mi) {
+            const Item nx = item_of(mi);
+            // (1) Dependencies first, while the compute warps are still busy with item mi-2/mi-1:
+            // they are normally satisfied a whole phase ahead, and the L2 round trips of the
+            // counter loads and of the two fences (~1.5k cycles each under load) stay off the
+            // critical path between "stage free" and the TMA issue.
+#ifdef HS_TILE_PROFILE
+            const long long prof_t0 = clock64();
+#endif
+            if (nx.p > 0) {
+                unsigned long long t0 = 0;
+                for (uint32_t spins = 0;; ++spins) {
+                    int dep = 0x7fffffff;             // lanes 0..8: one neighbour counter each
+                    if (lane < 9) {
+                        const int yy = nx.by + lane / 3 - 1, xx = nx.bx + lane % 3 - 1;
+                        if (yy >= 0 && yy < tg.tiles_y && xx >= 0 && xx < tg.tiles_x)
+                            dep = ld_relaxed_gpu(done + nx.b * per_img + yy * tg.tiles_x + xx);
                     }
-                    ++mi;
-                    progress = true;
+                    if (__reduce_min_sync(0xffffffffu, dep) >= nx.p) break;   // phase p-1 is complete around us
+                    if (np < mi && mbar_test(&stored[np & 1], (np >> 1) & 1)) {
+                        do_publish(np);
+                        ++np;
+                    }
+                    __nanosleep(64);
+                    if ((spins & 0xff) == 0xff) {
+                        const unsigned long long now = global_ns();
+                        if (t0 == 0) t0 = now;
+                        else if (now - t0 > WAIT_LIMIT_NS) __trap();
+                    }
+                }
+                if (lane == 0) {
+                    fence_acq_rel_gpu();              // acquire: the neighbours' stores are visible ...
+                    fence_proxy_async_all();          // ... also to the async proxy (TMA) reads issued below
                 }
             }
-            if (!progress) {
-                __nanosleep(32);
-                if ((++idle & 0x3ff) == 0) {
-                    const unsigned long long now = global_ns();
-                    if (t_idle == 0) t_idle = now;
-                    else if (now - t_idle > WAIT_LIMIT_NS) __trap();
+#ifdef HS_TILE_PROFILE
+            const long long prof_t1 = clock64();
+#endif
+            // (2) items <= mi-2 are stored by now or about to be: block on them, publish promptly
+            if (publish)
+                for (; np <= mi - 2; ++np) {
+                    mbar_wait(&stored[np & 1], (np >> 1) & 1);
+                    do_publish(np);
                 }
-            } else {
-                t_idle = 0;
+            // (3) the stage of item mi is free once the compute warps passed the barrier of item mi-1
+            if (mi >= 2) mbar_wait(&empty[mi & 1], ((mi - 2) >> 1) & 1);
+            if (lane == 0) {
+                issue(nx, mi & 1, true, true);
+#ifdef HS_TILE_PROFILE
+                if (mi >= 2) {
+                    g_tile_prof[blockIdx.x][7] += clock64() - reinterpret_cast<volatile long long*>(smem + TS::OFF_BAR + 48)[0];
+                    g_tile_prof[blockIdx.x][5] += prof_t1 - prof_t0;      // decode + dependency wait + fences
+                }
+#endif
             }
+            __syncwarp();
         }
+        if (publish)
+            for (; np < items; ++np) {
+                mbar_wait(&stored[np & 1], (np >> 1) & 1);
+                do_publish(np);
+            }
         return;
     }
 
@@ -601,7 +651,9 @@ k_jacobi_tile(const __grid_constant__ CUtensorMap tm_u0, const __grid_constant__
                 }
         }
 
+        HS_PROF_T(pt0);
         mbar_wait(&full[stage], (n >> 1) & 1);
+        HS_PROF_T(pt1);
 
         float u[R][4], v[R][4], ix[R][4], iy[R][4], it[R][4], iv[R][4];
 #pragma unroll
@@ -623,7 +675,11 @@ k_jacobi_tile(const __grid_constant__ CUtensorMap tm_u0, const __grid_constant__
         // dead - and (b) pulled this tile out of THIS stage, which now becomes the exchange scratch.
         fence_proxy_async();      // our generic-proxy scratch accesses of the other stage, before TMA rewrites it
         compute_sync<TS::CTHREADS>();
+#ifdef HS_TILE_PROFILE
+        if (tid == 0) reinterpret_cast<volatile long long*>(smem + TS::OFF_BAR + 48)[0] = clock64();
+#endif
         if (tid == 0 && n >= 1) mbar_arrive(&empty[stage ^ 1]);   // producer may refill it with item n+1
+        HS_PROF_T(pt2);
 
         float* s_ex = reinterpret_cast<float*>(st);
         const int kk = min(tg.k, tg.sweeps - cur.p * tg.k);
@@ -632,6 +688,7 @@ k_jacobi_tile(const __grid_constant__ CUtensorMap tm_u0, const __grid_constant__
         else
             tile_sweeps<RL, RR, R, NWARP, true>(u, v, ix, iy, it, iv, s_ex, kk, kf, warp, lane, inmask);
 
+        HS_PROF_T(pt3);
         // store the exact centre of the tile into the other pair of planes
         const int lx = lane * 4;
         if (lx >= tg.hxl && lx < tg.hxl + tg.vx && gx0 < g.W) {
@@ -652,6 +709,9 @@ k_jacobi_tile(const __grid_constant__ CUtensorMap tm_u0, const __grid_constant__
             __syncwarp();
             if (lane == 0) mbar_arrive(&stored[stage]);
         }
+        HS_PROF_T(pt4);
+        HS_PROF_ADD(0, pt0, pt1); HS_PROF_ADD(1, pt1, pt2); HS_PROF_ADD(2, pt2, pt3); HS_PROF_ADD(3, pt3, pt4);
+        HS_PROF_ADD(4, 0, 1);
     }
 }
 
