@@ -6,7 +6,7 @@ TAG=${1:-r01}
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > gpurun_out/${TAG}_gpu.txt
 echo "== pytest -m gpu"
-python -m pytest tests -m gpu -x -q 2>&1 | tail -15 | tee gpurun_out/${TAG}_pytest.txt
+timeout -s KILL 400 python -m pytest tests -m gpu -x -q 2>&1 | tail -15 | tee gpurun_out/${TAG}_pytest.txt
 echo "== smoke"
 python __graft_entry__.py smoke 2>&1 | tail -5 | tee gpurun_out/${TAG}_smoke.txt
 echo "== bench (1080p w=3, then w=5, 4k)"
@@ -17,12 +17,12 @@ python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/${TAG}_bench_
 tail -5 gpurun_out/${TAG}_bench.err
 echo "== ncu launch list"
 python bench.py --steps 2 --warmup 1 --no-cpu > gpurun_out/${TAG}_plain.log 2>&1 &&
-ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/${TAG}_launches.csv \
+ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file gpurun_out/${TAG}_launches.csv \
     python bench.py --steps 2 --warmup 1 --no-cpu > gpurun_out/${TAG}_ncu_list.log 2>&1
 echo "ncu list rc=$?"
 echo "== ncu full capture of the fused kernel"
-python bench.py --steps 1 --warmup 1 --no-cpu --iters 40 > gpurun_out/${TAG}_plain2.log 2>&1 &&
-ncu --set full --clock-control none --import-source on -k regex:k_jacobi_tile -s 12 -c 3 -f -o gpurun_out/${TAG}_prof_tile \
-    python bench.py --steps 1 --warmup 1 --no-cpu --iters 40 > gpurun_out/${TAG}_ncu_full.log 2>&1
+python bench.py --steps 1 --warmup 1 --no-cpu --iters 120 > gpurun_out/${TAG}_plain2.log 2>&1 &&
+ncu --set full --clock-control none --import-source on -k regex:k_jacobi_tile -s 2 -c 2 -f -o gpurun_out/${TAG}_prof_tile \
+    python bench.py --steps 1 --warmup 1 --no-cpu --iters 120 > gpurun_out/${TAG}_ncu_full.log 2>&1
 echo "ncu full rc=$?"
 ls -la gpurun_out | tail -20

@@ -51,8 +51,8 @@ if os.path.exists(rp):
             "smsp__average_warp_latency_per_inst_issued.ratio"] + \
            [h for h in hdr if h.startswith("smsp__average_warps_issue_stalled_") and h.endswith("_per_issue_active.ratio")]
     with open(os.path.join(out_dir, f"{tag}_tile_kernel_ncu.txt"), "w") as f:
-        f.write(f"# ncu --set full --clock-control none --import-source on -k regex:k_jacobi_tile -s 12 -c 3\n"
-                f"# command: python bench.py --steps 1 --warmup 1 --no-cpu --iters 40   (1080p, w=3)\n"
+        f.write(f"# ncu --set full --clock-control none --import-source on -k regex:k_jacobi_tile -s 2 -c 2\n"
+                f"# command: python bench.py --steps 1 --warmup 1 --no-cpu --iters 120   (1080p, w=3; one launch = 120 sweeps)\n"
                 f"# one column per captured launch; ncu flushes caches between replays, so DRAM bytes are cold-cache\n")
         for w in want:
             if w in hdr:
