@@ -150,7 +150,7 @@ struct Tile {
     // One launch advances `sweeps` sweeps in phases of k.  phases > 1 needs every CTA resident at
     // once (they wait on each other's tiles) -> cooperative launch; a single phase is chained to
     // the previous launch with programmatic dependent launch instead.
-    static cudaError_t launch(hs_ctx* c, int k, int sweeps) {
+    static cudaError_t launch(hs_ctx* c, int k, int sweeps, int row0, int row1) {
         hs::TileGrid tg;
         tg.k = k;
         tg.sweeps = sweeps;
@@ -159,7 +159,7 @@ struct Tile {
         tg.vx = TS::SX - tg.hxl - round_up(RR * k, 4);
         tg.vy = TS::SY - tg.hyt - RR * k;
         tg.tiles_x = (c->W + tg.vx - 1) / tg.vx;
-        tg.tiles_y = (c->oy1 - c->oy0 + tg.vy - 1) / tg.vy;
+        tg.tiles_y = (row1 - row0 + tg.vy - 1) / tg.vy;
         tg.ntiles = tg.tiles_x * tg.tiles_y * c->B;
         const int phases = (sweeps + k - 1) / k;
         const int grid = std::min(tg.ntiles, c->num_sms);      // persistent: one CTA per SM
@@ -185,8 +185,11 @@ struct Tile {
         cfg.attrs = attr;
         cfg.numAttrs = 1;
         const int a = c->cur, b = c->cur ^ 1;
+        hs::Geom g = c->geom();
+        g.oy0 = row0;                                          // rows this launch produces
+        g.oy1 = row1;
         return cudaLaunchKernelEx(&cfg, kernel(), c->tm_u[a], c->tm_v[a], c->tm_u[b], c->tm_v[b], c->tm_cpk,
-                                  c->tm_inv, c->d_u[a], c->d_v[a], c->d_u[b], c->d_v[b], c->d_done, c->geom(),
+                                  c->tm_inv, c->d_u[a], c->d_v[a], c->d_u[b], c->d_v[b], c->d_done, g,
                                   tg, kf);
     }
     static size_t max_tiles(const hs_ctx* c) {                 // upper bound over all k (k = 1 tiles are the largest)
@@ -276,7 +279,7 @@ int do_iterate(hs_ctx* c, int iters) {
             // everything in one multi-phase launch, unless the caller must refresh halos between
             // fused launches (row slabs) or asked for per-launch behaviour
             step = c->multi_phase ? left : std::min(c->k, left);
-            tile_dispatch(c->RL, c->RR, [&](auto t) { e = decltype(t)::launch(c, std::min(c->k, step), step); });
+            tile_dispatch(c->RL, c->RR, [&](auto t) { e = decltype(t)::launch(c, std::min(c->k, step), step, c->oy0, c->oy1); });
             if (e == cudaSuccess && (((step + c->k - 1) / c->k) & 1)) c->cur ^= 1;
         } else {
             dim3 block(32, 8);
@@ -509,6 +512,22 @@ int hs_iterate(hs_ctx* c, int iterations) {
     if (!c) return HS_ERR_INVALID_ARG;
     DevGuard g(c->dev);
     return do_iterate(c, iterations);
+}
+
+int hs_iterate_rows(hs_ctx* c, int sweeps, int row_begin, int row_end, int flip) {
+    if (!c) return HS_ERR_INVALID_ARG;
+    if (!c->prepared) return fail(c, HS_ERR_STATE, "hs_iterate_rows before hs_prepare");
+    if (c->kernel_id != 1) return fail(c, HS_ERR_UNSUPPORTED, "hs_iterate_rows needs the fused kernel (window 2..5)");
+    if (sweeps < 1 || sweeps > c->k) return fail(c, HS_ERR_INVALID_ARG, "sweeps must be in [1, temporal_k=%d]", c->k);
+    if (row_begin < c->oy0 || row_end > c->oy1 || row_begin >= row_end)
+        return fail(c, HS_ERR_INVALID_ARG, "rows [%d,%d) not inside the output rows [%d,%d)", row_begin, row_end, c->oy0, c->oy1);
+    DevGuard g(c->dev);
+    cudaError_t e = cudaSuccess;
+    tile_dispatch(c->RL, c->RR, [&](auto t) { e = decltype(t)::launch(c, sweeps, sweeps, row_begin, row_end); });
+    if (e != cudaSuccess) return fail(c, HS_ERR_CUDA, "sweep launch failed: %s", cudaGetErrorString(e));
+    c->timing.launches += 1;
+    if (flip) c->cur ^= 1;
+    return HS_OK;
 }
 
 int hs_solve_device(hs_ctx* c) {

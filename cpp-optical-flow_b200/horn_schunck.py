@@ -145,6 +145,9 @@ class Solver:
     def iterate(self, iterations):
         self._check(self._lib.hs_iterate(self._ctx, int(iterations)))
 
+    def iterate_rows(self, sweeps, row_begin, row_end, flip):
+        self._check(self._lib.hs_iterate_rows(self._ctx, int(sweeps), int(row_begin), int(row_end), int(bool(flip))))
+
     def solve_device(self):
         self._check(self._lib.hs_solve_device(self._ctx))
 

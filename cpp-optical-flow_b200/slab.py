@@ -135,6 +135,7 @@ class DeviceSlab:
         # send/recv, so launches and halo exchanges are ordered on the device without host syncs.
         # (A NULL stream in hs_config means "private stream", so the default stream cannot be used.)
         self.stream = torch.cuda.Stream(device=self._device)
+        self.comm_stream = torch.cuda.Stream(device=self._device)   # halo exchange, overlapped with interior rows
         flags = (H.FLAG_TOP_IS_SEAM if geom.top_seam else 0) | (H.FLAG_BOTTOM_IS_SEAM if geom.bottom_seam else 0)
         self.solver = Solver(geom.width, geom.rows, geom.window, iterations, alpha, device=device,
                              temporal_k=geom.k, flags=flags, out_rows=geom.out_rows, stream=self.stream.cuda_stream)
@@ -161,20 +162,49 @@ class DeviceSlab:
             out.append(self._views[ptr])
         return out
 
-    def run(self, exchange=exchange_halos, group=None):
+    def run(self, exchange=exchange_halos, group=None, overlap=True):
         """prepare + `iterations` sweeps, exchanging halos after every fused launch but the last.
-        Asynchronous: everything is queued on self.stream."""
+        Asynchronous: everything is queued on self.stream (and self.comm_stream).
+
+        overlap=True: per fused launch the rows next to a seam are produced first (two thin strip
+        launches), their exchange runs on a second stream, and the interior rows - the bulk of the
+        work - are computed meanwhile; the next launch waits for both."""
+        torch = self._torch
+        g = self.geom
+        rl, rr = radii(g.window)
+        o0, o1 = g.out_rows
+        strip = max(rl, rr) * self.k                       # rows a neighbour reads from us
+        overlap = overlap and g.world > 1 and (o1 - o0) >= 4 * strip and strip > 0
         launches = 0
-        with self._torch.cuda.stream(self.stream):
+        with torch.cuda.stream(self.stream):
             self.solver.prepare()
             left = self.iterations
             while left > 0:
                 kk = min(self.k, left)
-                self.solver.iterate(kk)
                 left -= kk
-                launches += 1
-                if left > 0 and self.geom.world > 1:
-                    exchange(self.geom, self.planes(), group)
+                if not (overlap and left > 0):
+                    self.solver.iterate(kk)
+                    launches += 1
+                    if left > 0 and g.world > 1:
+                        exchange(g, self.planes(), group)
+                    continue
+                top, bot = g.top_seam, g.bottom_seam
+                a = o0 + (strip if top else 0)
+                b = o1 - (strip if bot else 0)
+                if top:
+                    self.solver.iterate_rows(kk, o0, a, False)
+                if bot:
+                    self.solver.iterate_rows(kk, b, o1, False)
+                strips_done = torch.cuda.Event()
+                strips_done.record(self.stream)
+                self.solver.iterate_rows(kk, a, b, True)        # interior; flips the planes
+                launches += 1 + int(top) + int(bot)
+                with torch.cuda.stream(self.comm_stream):
+                    self.comm_stream.wait_event(strips_done)
+                    exchange(g, self.planes(), group)           # planes() = the NEW planes now
+                    exchanged = torch.cuda.Event()
+                    exchanged.record(self.comm_stream)
+                self.stream.wait_event(exchanged)
         return launches
 
     def download(self, dtype=np.float32):

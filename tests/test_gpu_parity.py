@@ -201,6 +201,20 @@ def test_row_slabs_equal_single_solve(pkg, w, k, nslab):
     assert np.array_equal(u, su) and np.array_equal(v, sv)
 
 
+def test_partial_row_launches_compose_to_a_full_launch(pkg):
+    """hs_iterate_rows (the overlap helper of the row-slab path): strips + interior == one launch."""
+    a, b = rand_pair((300, 260), 77)
+    with pkg.Solver(260, 300, 3, 12, 1.0, temporal_k=4) as s:
+        s.upload(a, b); s.prepare(); s.iterate(12); u, v = s.download(np.float32)
+        s.prepare()
+        for _ in range(3):
+            s.iterate_rows(4, 0, 7, False)
+            s.iterate_rows(4, 280, 300, False)
+            s.iterate_rows(4, 7, 280, True)
+        u2, v2 = s.download(np.float32)
+    assert np.array_equal(u, u2) and np.array_equal(v, v2)
+
+
 # ---------------------------------------------------------------- BASELINE configs at full size
 @pytest.mark.parametrize("w", [3, 5])
 def test_config2_1080p_full_size(pkg, c_oracle, w):
