@@ -519,8 +519,9 @@ int hs_iterate_rows(hs_ctx* c, int sweeps, int row_begin, int row_end, int flip)
     if (!c->prepared) return fail(c, HS_ERR_STATE, "hs_iterate_rows before hs_prepare");
     if (c->kernel_id != 1) return fail(c, HS_ERR_UNSUPPORTED, "hs_iterate_rows needs the fused kernel (window 2..5)");
     if (sweeps < 1 || sweeps > c->k) return fail(c, HS_ERR_INVALID_ARG, "sweeps must be in [1, temporal_k=%d]", c->k);
-    if (row_begin < c->oy0 || row_end > c->oy1 || row_begin >= row_end)
-        return fail(c, HS_ERR_INVALID_ARG, "rows [%d,%d) not inside the output rows [%d,%d)", row_begin, row_end, c->oy0, c->oy1);
+    // any rows of the buffer may be produced: a deep-halo row slab also advances (part of) its halo
+    if (row_begin < 0 || row_end > c->H || row_begin >= row_end)
+        return fail(c, HS_ERR_INVALID_ARG, "rows [%d,%d) not inside the buffer rows [0,%d)", row_begin, row_end, c->H);
     DevGuard g(c->dev);
     cudaError_t e = cudaSuccess;
     tile_dispatch(c->RL, c->RR, [&](auto t) { e = decltype(t)::launch(c, sweeps, sweeps, row_begin, row_end); });

@@ -8,6 +8,12 @@ planes, so a halo is one contiguous send, no packing kernel.  Coefficients are n
 every rank gets the frame rows of its band + halo (+1 seam row for the Sobel taps) and recomputes
 them.  The result is bit-identical to the single-GPU solve (Jacobi has no ordering freedom).
 
+Deep halos: with `depth` d the slab keeps d*a*k / d*(w/2)*k halo rows and exchanges them only
+every d fused launches; launch j of such a cycle also advances the d-1-j halo layers that later
+launches of the cycle still read (a fraction of a percent of redundant rows).  That divides the
+number of exchanges - and of host round trips through Python/NCCL, which is what bounds 8 GPUs,
+where a launch is only ~270 us of device time - by d.
+
 The exchange logic is written against torch tensors only, so the same code runs on CPU tensors
 with the gloo backend in tests/test_slab_gloo.py.
 """
@@ -45,7 +51,8 @@ class SlabGeometry:
     height: int          # full image
     width: int
     window: int
-    k: int               # sweeps fused per launch == sweeps between halo exchanges
+    k: int               # sweeps fused per launch
+    depth: int           # fused launches between two halo exchanges (halo = depth * radius * k rows)
     y0: int              # owned rows [y0, y1) in image coordinates
     y1: int
     b0: int              # buffer rows [b0, b1) = owned rows + halos, clipped to the image
@@ -73,19 +80,30 @@ class SlabGeometry:
         return self.b1 - self.b0
 
 
-def plan(height: int, width: int, world: int, rank: int, window: int, k: int) -> SlabGeometry:
+def plan(height: int, width: int, world: int, rank: int, window: int, k: int, depth: int = 1) -> SlabGeometry:
     rl, rr = radii(window)
     bounds = partition_rows(height, world)
     y0, y1 = bounds[rank]
-    need = max(rl, rr) * k
+    need = max(rl, rr) * k * depth
     if world > 1 and min(b - a for a, b in bounds) < need:
         raise ValueError(f"row slabs of {min(b - a for a, b in bounds)} rows are thinner than the {need}-row halo "
-                         f"(window {window}, k {k}); use fewer ranks or a smaller k")
-    b0 = max(0, y0 - rl * k) if rank > 0 else y0
-    b1 = min(height, y1 + rr * k) if rank < world - 1 else y1
+                         f"(window {window}, k {k}, depth {depth}); use fewer ranks, a smaller k or depth")
+    b0 = max(0, y0 - rl * k * depth) if rank > 0 else y0
+    b1 = min(height, y1 + rr * k * depth) if rank < world - 1 else y1
     top_seam, bottom_seam = b0 > 0, b1 < height
-    return SlabGeometry(rank, world, height, width, window, k, y0, y1, b0, b1,
+    return SlabGeometry(rank, world, height, width, window, k, depth, y0, y1, b0, b1,
                         b0 - (1 if top_seam else 0), b1 + (1 if bottom_seam else 0), top_seam, bottom_seam)
+
+
+def cycle_rows(geom: SlabGeometry, j: int, launches: int):
+    """Buffer rows launch j (0-based) of an exchange cycle of `launches` fused launches has to
+    produce: the owned rows plus the halo layers the remaining launches of the cycle still read."""
+    rl, rr = radii(geom.window)
+    ext = launches - 1 - j
+    o0, o1 = geom.out_rows
+    r0 = max(0, o0 - ext * rl * geom.k) if geom.rank > 0 else o0
+    r1 = min(geom.rows, o1 + ext * rr * geom.k) if geom.rank < geom.world - 1 else o1
+    return r0, r1
 
 
 def exchange_halos(geom: SlabGeometry, planes, group=None):
@@ -93,7 +111,7 @@ def exchange_halos(geom: SlabGeometry, planes, group=None):
     v of this rank) from the neighbours' owned rows.  Neighbour-only send/recv, one batch."""
     import torch.distributed as dist
     rl, rr = radii(geom.window)
-    up, dn = rl * geom.k, rr * geom.k         # rows this rank needs from above / from below
+    up, dn = rl * geom.k * geom.depth, rr * geom.k * geom.depth   # rows needed from above / below
     o0, o1 = geom.out_rows
     ops = []
     for t in planes:
@@ -163,68 +181,74 @@ class DeviceSlab:
         return out
 
     def run(self, exchange=exchange_halos, group=None, overlap=True):
-        """prepare + `iterations` sweeps, exchanging halos after every fused launch but the last.
+        """prepare + `iterations` sweeps; halos are exchanged after every `depth` fused launches.
         Asynchronous: everything is queued on self.stream (and self.comm_stream).
 
-        overlap=True: per fused launch the rows next to a seam are produced first (two thin strip
-        launches), their exchange runs on a second stream, and the interior rows - the bulk of the
-        work - are computed meanwhile; the next launch waits for both."""
+        overlap: on the last launch of a cycle the rows the neighbours read are produced first (two
+        thin strip launches), their exchange runs on a second stream, and the interior rows - the
+        bulk of the work - are computed meanwhile; the next launch waits for both."""
         torch = self._torch
         g = self.geom
         rl, rr = radii(g.window)
         o0, o1 = g.out_rows
-        strip = max(rl, rr) * self.k                       # rows a neighbour reads from us
+        strip = max(rl, rr) * self.k * g.depth              # rows a neighbour reads from us
         overlap = overlap and g.world > 1 and (o1 - o0) >= 4 * strip and strip > 0
         launches = 0
         with torch.cuda.stream(self.stream):
             self.solver.prepare()
             left = self.iterations
             while left > 0:
-                kk = min(self.k, left)
-                left -= kk
-                if not (overlap and left > 0):
-                    self.solver.iterate(kk)
-                    launches += 1
-                    if left > 0 and g.world > 1:
+                cyc = min(g.depth, (left + self.k - 1) // self.k)       # fused launches of this cycle
+                for j in range(cyc):
+                    kk = min(self.k, left)
+                    left -= kk
+                    r0, r1 = cycle_rows(g, j, cyc)
+                    last = j == cyc - 1
+                    if g.world == 1 or not (last and left > 0):
+                        self.solver.iterate_rows(kk, r0, r1, True)     # mid-cycle, or nothing follows
+                        launches += 1
+                    elif not overlap:
+                        self.solver.iterate_rows(kk, r0, r1, True)
+                        launches += 1
                         exchange(g, self.planes(), group)
-                    continue
-                top, bot = g.top_seam, g.bottom_seam
-                a = o0 + (strip if top else 0)
-                b = o1 - (strip if bot else 0)
-                if top:
-                    self.solver.iterate_rows(kk, o0, a, False)
-                if bot:
-                    self.solver.iterate_rows(kk, b, o1, False)
-                strips_done = torch.cuda.Event()
-                strips_done.record(self.stream)
-                self.solver.iterate_rows(kk, a, b, True)        # interior; flips the planes
-                launches += 1 + int(top) + int(bot)
-                with torch.cuda.stream(self.comm_stream):
-                    self.comm_stream.wait_event(strips_done)
-                    exchange(g, self.planes(), group)           # planes() = the NEW planes now
-                    exchanged = torch.cuda.Event()
-                    exchanged.record(self.comm_stream)
-                self.stream.wait_event(exchanged)
+                    else:                                               # r0, r1 == o0, o1 here
+                        top, bot = g.top_seam, g.bottom_seam
+                        a = o0 + (strip if top else 0)
+                        b = o1 - (strip if bot else 0)
+                        if top:
+                            self.solver.iterate_rows(kk, o0, a, False)
+                        if bot:
+                            self.solver.iterate_rows(kk, b, o1, False)
+                        strips_done = torch.cuda.Event()
+                        strips_done.record(self.stream)
+                        self.solver.iterate_rows(kk, a, b, True)        # interior; flips the planes
+                        launches += 1 + int(top) + int(bot)
+                        with torch.cuda.stream(self.comm_stream):
+                            self.comm_stream.wait_event(strips_done)
+                            exchange(g, self.planes(), group)           # planes() = the NEW planes now
+                            exchanged = torch.cuda.Event()
+                            exchanged.record(self.comm_stream)
+                        self.stream.wait_event(exchanged)
         return launches
 
     def download(self, dtype=np.float32):
         return self.solver.download(dtype)
 
 
-def solve_slabs_single_process(prev, nxt, window, iterations, alpha, nslab, temporal_k=0, device=0):
-    """N slab contexts on ONE GPU, halos copied device-to-device by the host between launches.
-    Exercises exactly the kernels / row ranges / seam handling of the multi-GPU path (used by the
-    GPU tests; never run waiting kernels of several ranks concurrently on one GPU)."""
+def solve_slabs_single_process(prev, nxt, window, iterations, alpha, nslab, temporal_k=0, device=0, depth=1):
+    """N slab contexts on ONE GPU, halos copied device-to-device by the host between exchange
+    cycles.  Exercises exactly the kernels / row ranges / seam handling of the multi-GPU path (used
+    by the GPU tests; never run waiting kernels of several ranks concurrently on one GPU)."""
     import torch
     from .horn_schunck import Solver
     H, W = prev.shape
     probe = Solver(W, max(H // nslab, 1), window, iterations, alpha, device=device, temporal_k=temporal_k)
     k = probe.timing().temporal_k
     probe.close()
-    geoms = [plan(H, W, nslab, r, window, k) for r in range(nslab)]
+    geoms = [plan(H, W, nslab, r, window, k, depth) for r in range(nslab)]
     slabs = [DeviceSlab(g, iterations, alpha, device) for g in geoms]
     rl, rr = radii(window)
-    up, dn = rl * k, rr * k
+    up, dn = rl * k * depth, rr * k * depth
     try:
         for s in slabs:
             g = s.geom
@@ -232,10 +256,13 @@ def solve_slabs_single_process(prev, nxt, window, iterations, alpha, nslab, temp
             s.solver.prepare()
         left = iterations
         while left > 0:
-            kk = min(k, left)
-            for s in slabs:
-                s.solver.iterate(kk)
-            left -= kk
+            cyc = min(depth, (left + k - 1) // k)
+            for j in range(cyc):
+                kk = min(k, left)
+                left -= kk
+                for s in slabs:
+                    r0, r1 = cycle_rows(s.geom, j, cyc)
+                    s.solver.iterate_rows(kk, r0, r1, True)
             if left > 0:
                 for s in slabs:
                     s.solver.sync()
@@ -266,7 +293,8 @@ def bench_slab(args, rank, local_rank, world, metric, algo_bytes, peak_fn):
     window = args.window
     rl, rr = radii(window)
     k = args.k or max(1, 6 // max(1, max(rl, rr)))
-    geom = plan(H, W, world, rank, window, k)
+    depth = int(os.environ.get("HS_SLAB_DEPTH", 0)) or (2 if world >= 8 else 1)
+    geom = plan(H, W, world, rank, window, k, depth)
     dev = torch.device("cuda", local_rank)
     prev, nxt = synth.frame_pair(geom.f1 - geom.f0, W, y0=geom.f0)
     slab = DeviceSlab(geom, T, 1.0, local_rank)
@@ -310,7 +338,8 @@ def bench_slab(args, rank, local_rank, world, metric, algo_bytes, peak_fn):
                 "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": {"workload": f"slab16k: one {W}x{H} pair, {T} sweeps, row slabs", "window": window,
                            "alpha": 1.0, "iterations": T, "temporal_k": k,
-                           "parallelism": f"{world} row slabs, {rl * k}+{rr * k} halo rows per seam every {k} sweeps",
+                           "parallelism": f"{world} row slabs, {rl * k * depth}+{rr * k * depth} halo rows per seam "
+                                          f"every {k * depth} sweeps (halo depth {depth} launches)",
                            "l2": "inputs (GBs per GPU) exceed L2; 512 MiB memset before every step anyway"},
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                              "frac": achieved / peak, "traffic": None, "peak_source": src,

@@ -144,10 +144,12 @@ int hs_upload(hs_ctx* ctx,                                    /* host uint8 -> d
               const uint8_t* next, size_t next_row_stride, size_t next_image_stride);
 int hs_prepare(hs_ctx* ctx);                                  /* gradients+coefficients, u=v=0   */
 int hs_iterate(hs_ctx* ctx, int iterations);                  /* `iterations` more Jacobi sweeps */
-/* Row-slab overlap helper: `sweeps` (<= temporal_k) fused sweeps producing only buffer rows
- * [row_begin, row_end) of the NEXT flow planes; the current planes become the next ones when
- * `flip` is non-zero (pass it on the last partial launch of a step).  Lets the host compute the
- * rows next to a seam first, start their halo exchange, and overlap it with the interior rows. */
+/* Row-slab helper: `sweeps` (<= temporal_k) fused sweeps producing only buffer rows
+ * [row_begin, row_end) of the NEXT flow planes (any rows of the buffer, halo rows included); the
+ * current planes become the next ones when `flip` is non-zero (pass it on the last partial launch
+ * of a step).  Lets the host (a) compute the rows next to a seam first, start their halo exchange
+ * and overlap it with the interior rows, and (b) keep a halo several launches deep and advance
+ * part of it redundantly, so that halos are exchanged only every few launches. */
 int hs_iterate_rows(hs_ctx* ctx, int sweeps, int row_begin, int row_end, int flip);
 int hs_solve_device(hs_ctx* ctx);                             /* prepare + iterate(max_iterations)*/
 int hs_download(hs_ctx* ctx,                                  /* device u,v -> host              */

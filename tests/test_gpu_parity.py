@@ -189,15 +189,16 @@ def test_f32_and_f64_outputs_agree(pkg):
 
 
 # ---------------------------------------------------------------- row slabs (one context per slab)
-@pytest.mark.parametrize("w,k,nslab", [(3, 4, 2), (3, 3, 3), (5, 2, 2), (4, 2, 3), (3, 1, 4)])
-def test_row_slabs_equal_single_solve(pkg, w, k, nslab):
+@pytest.mark.parametrize("w,k,nslab,depth", [(3, 4, 2, 1), (3, 3, 3, 1), (5, 2, 2, 1), (4, 2, 3, 1), (3, 1, 4, 1),
+                                             (3, 4, 2, 2), (3, 2, 3, 3), (5, 2, 2, 2), (4, 2, 2, 2)])
+def test_row_slabs_equal_single_solve(pkg, w, k, nslab, depth):
     """N slab contexts on one GPU with host-side halo copies == one whole-image solve, bit for bit."""
     from cpp_optical_flow_b200 import slab
     a, b = rand_pair((260, 300), seed=w + k)
     iters = 3 * k + 2
     with pkg.Solver(300, 260, w, iters, 1.0, temporal_k=k) as s:
         u, v = s.solve(a, b, np.float32)
-    su, sv = slab.solve_slabs_single_process(a, b, w, iters, 1.0, nslab, temporal_k=k)
+    su, sv = slab.solve_slabs_single_process(a, b, w, iters, 1.0, nslab, temporal_k=k, depth=depth)
     assert np.array_equal(u, su) and np.array_equal(v, sv)
 
 
