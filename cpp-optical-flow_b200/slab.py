@@ -293,7 +293,7 @@ def bench_slab(args, rank, local_rank, world, metric, algo_bytes, peak_fn):
     window = args.window
     rl, rr = radii(window)
     k = args.k or max(1, 6 // max(1, max(rl, rr)))
-    depth = int(os.environ.get("HS_SLAB_DEPTH", 0)) or (2 if world >= 8 else 1)
+    depth = int(os.environ.get("HS_SLAB_DEPTH", 0)) or (3 if world >= 8 else (2 if world >= 4 else 1))
     geom = plan(H, W, world, rank, window, k, depth)
     dev = torch.device("cuda", local_rank)
     prev, nxt = synth.frame_pair(geom.f1 - geom.f0, W, y0=geom.f0)
