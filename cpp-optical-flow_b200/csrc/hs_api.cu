@@ -48,7 +48,7 @@ struct hs_ctx {
     double alpha = 0;
     int pitch = 0;
     long long plane = 0;
-    int oy0 = 0, oy1 = 0;
+    int oy0 = 0, oy1 = 0, grow0 = 0;
     bool top_seam = false, bot_seam = false;
 
     int frows = 0, frow0 = 0;
@@ -79,7 +79,7 @@ struct hs_ctx {
 
     hs::Geom geom() const {
         hs::Geom g;
-        g.W = W; g.H = H; g.pitch = pitch; g.plane = plane; g.oy0 = oy0; g.oy1 = oy1;
+        g.W = W; g.H = H; g.pitch = pitch; g.plane = plane; g.oy0 = oy0; g.oy1 = oy1; g.grow0 = grow0;
         return g;
     }
 };
@@ -146,7 +146,7 @@ struct Tile {
     static cudaError_t configure() {
         return cudaFuncSetAttribute(kernel(), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TS::SMEM);
     }
-    static int max_k() { return (TS::SY - 1) / std::max(1, RL + RR); }
+    static int max_k() { return (TS::SY - 3) / std::max(1, RL + RR); }
     // One launch advances `sweeps` sweeps in phases of k.  phases > 1 needs every CTA resident at
     // once (they wait on each other's tiles) -> cooperative launch; a single phase is chained to
     // the previous launch with programmatic dependent launch instead.
@@ -155,9 +155,13 @@ struct Tile {
         tg.k = k;
         tg.sweeps = sweeps;
         tg.hxl = round_up(RL * k, 4);
-        tg.hyt = RL * k;
         tg.vx = TS::SX - tg.hxl - round_up(RR * k, 4);
-        tg.vy = TS::SY - tg.hyt - RR * k;
+        // every staged tile must start on an EVEN image row (the canonical column sums pair rows
+        // (2i, 2i+1), and a thread's 4-row patch shares those pair sums): one more halo row above
+        // when needed, and an even tile pitch
+        tg.hyt = RL * k + ((row0 + c->grow0 + RL * k) & 1);
+        tg.vy = (TS::SY - tg.hyt - RR * k) & ~1;
+        if (tg.vx <= 0 || tg.vy <= 0) return cudaErrorInvalidValue;
         tg.tiles_x = (c->W + tg.vx - 1) / tg.vx;
         tg.tiles_y = (row1 - row0 + tg.vy - 1) / tg.vy;
         tg.ntiles = tg.tiles_x * tg.tiles_y * c->B;
@@ -195,7 +199,7 @@ struct Tile {
     static size_t max_tiles(const hs_ctx* c) {                 // upper bound over all k (k = 1 tiles are the largest)
         size_t best = 0;
         for (int k = 1; k <= max_k(); ++k) {
-            const int vx = TS::SX - round_up(RL * k, 4) - round_up(RR * k, 4), vy = TS::SY - (RL + RR) * k;
+            const int vx = TS::SX - round_up(RL * k, 4) - round_up(RR * k, 4), vy = (TS::SY - (RL + RR) * k - 1) & ~1;
             if (vx <= 0 || vy <= 0) break;
             const size_t n = (size_t)((c->W + vx - 1) / vx) * ((c->oy1 - c->oy0 + vy - 1) / vy) * c->B;
             best = std::max(best, n);
@@ -390,6 +394,7 @@ int hs_create(const hs_config* cfg_in, hs_ctx** out) {
     c->RL = c->a; c->RR = c->w - 1 - c->a;
     c->oy0 = cfg.out_row_begin; c->oy1 = cfg.out_row_end;
     if (c->oy0 == 0 && c->oy1 == 0) c->oy1 = c->H;
+    c->grow0 = cfg.global_row0;
     c->top_seam = cfg.flags & HS_FLAG_TOP_IS_SEAM;
     c->bot_seam = cfg.flags & HS_FLAG_BOTTOM_IS_SEAM;
     c->pitch = round_up(c->W, 32);

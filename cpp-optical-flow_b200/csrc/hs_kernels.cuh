@@ -7,8 +7,14 @@
 //   K5  k_widen / k_unpack_grad <- CV_64FC1 outputs (:49-50; plotFlow.cpp:72-75 reads double)
 //
 // Canonical arithmetic (every kernel uses exactly this, so all variants are bit-identical):
-//   row sum  h(y,x)  = ((t[x-a] + t[x-a+1]) + ...) + t[x-a+w-1]      left to right, zeros outside
-//   box sum  S(y,x)  = ((h[y-a] + h[y-a+1]) + ...) + h[y-a+w-1]      top to bottom
+//   window sums are PAIRED: along a row, neighbours are first added in pairs that start at EVEN
+//   absolute columns, a window that starts at an odd column / ends at an even one contributes that
+//   element alone, and the terms are then added left to right, zeros outside the image:
+//       w=3, x even:  t[x-1] + (t[x] + t[x+1])          w=3, x odd:  (t[x-1] + t[x]) + t[x+1]
+//       w=5, x even:  ((t[x-2]+t[x-1]) + (t[x]+t[x+1])) + t[x+2]      x odd:  (t[x-2] + (..)) + (..)
+//   the same rule combines the row sums down a column (pairs start at even absolute rows).  A pair
+//   sum is shared by the two windows that contain it: 1.5 instead of 2 adds per pixel and
+//   direction for w=3, 2.5 instead of 4 for w=5.
 //   ubar = S_u * fl(1/w^2);  vbar likewise
 //   t = fma(Ix, ubar, fma(Iy, vbar, It));  c = t * inv;  u' = fma(-Ix, c, ubar);  v' = fma(-Iy, c, vbar)
 // with inv = 1 / (fl(alpha^2) + (Ix^2 + Iy^2)) rounded once (IEEE division) in K1.
@@ -29,6 +35,7 @@ struct Geom {
     int pitch;      // pixels per buffer row (multiple of 32)
     long long plane;  // pixels between consecutive pairs of the batch (pitch * H)
     int oy0, oy1;   // rows this context produces: [oy0, oy1)
+    int grow0;      // image row of buffer row 0 (row slabs); only its parity matters (pair alignment)
 };
 
 // Gradient coefficients are exact small integers (|Ix|,|Iy| <= 1020, |It| <= 255), so the three of
@@ -137,23 +144,33 @@ k_jacobi_generic(const float* __restrict__ u, const float* __restrict__ v,
     const size_t base = (size_t)blockIdx.z * g.plane;
     const float* U = u + base;
     const float* V = v + base;
-    float su = 0.f, sv = 0.f;
-    for (int dy = 0; dy < w; ++dy) {
-        const int yy = y + dy - a;
+    // canonical paired sums, written as plain loops (see the header comment)
+    auto row_sum = [&](const float* P, int yy) {            // sum over columns x-a .. x-a+w-1 of row yy
         const bool yin = (yy >= 0) && (yy < g.H);
-        const size_t ro = (size_t)(yin ? yy : 0) * g.pitch;
-        float hu = 0.f, hv = 0.f;
-        for (int dx = 0; dx < w; ++dx) {
-            const int xx = x + dx - a;
-            const bool in = yin && (xx >= 0) && (xx < g.W);
-            const float tu = in ? U[ro + xx] : 0.f;
-            const float tv = in ? V[ro + xx] : 0.f;
-            hu = (dx == 0) ? tu : __fadd_rn(hu, tu);
-            hv = (dx == 0) ? tv : __fadd_rn(hv, tv);
-        }
-        su = (dy == 0) ? hu : __fadd_rn(su, hu);
-        sv = (dy == 0) ? hv : __fadd_rn(sv, hv);
-    }
+        const float* row = P + (size_t)(yin ? yy : 0) * g.pitch;
+        auto tap = [&](int xx) { return (yin && xx >= 0 && xx < g.W) ? row[xx] : 0.f; };
+        int col = x - a;
+        const int hi = col + w - 1;
+        float s = 0.f;
+        bool first = true;
+        auto add = [&](float t) { s = first ? t : __fadd_rn(s, t); first = false; };
+        if (col & 1) { add(tap(col)); ++col; }
+        for (; col + 1 <= hi; col += 2) add(__fadd_rn(tap(col), tap(col + 1)));
+        if (col == hi) add(tap(col));
+        return s;
+    };
+    auto box_sum = [&](const float* P) {                    // the same rule down the rows y-a .. y-a+w-1
+        int r = y - a;
+        const int hi = r + w - 1;
+        float s = 0.f;
+        bool first = true;
+        auto add = [&](float t) { s = first ? t : __fadd_rn(s, t); first = false; };
+        if ((r + g.grow0) & 1) { add(row_sum(P, r)); ++r; }
+        for (; r + 1 <= hi; r += 2) add(__fadd_rn(row_sum(P, r), row_sum(P, r + 1)));
+        if (r == hi) add(row_sum(P, r));
+        return s;
+    };
+    const float su = box_sum(U), sv = box_sum(V);
     const size_t o = base + (size_t)y * g.pitch + x;
     float ix, iy, it, nu, nv;
     unpack_coef(cpk[o], ix, iy, it);
@@ -302,23 +319,65 @@ struct TileShape {
     }
 };
 
-// row sums of one patch row: 4 outputs from 4 own values + RL left + RR right neighbours
+// Does any of the 4 outputs of a 4-aligned group use the single element / the pair starting at
+// local position `pos` (may be negative or >= 4)?  Walks the pairing rule at compile time.
 template <int RL, int RR>
-__device__ __forceinline__ void row_sums(const float (&a)[4], float (&h)[4]) {
-    float e[4 + RL + RR];
-#pragma unroll
-    for (int i = 0; i < RL; ++i) e[i] = __shfl_up_sync(0xffffffffu, a[4 - RL + i], 1);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) e[RL + i] = a[i];
-#pragma unroll
-    for (int i = 0; i < RR; ++i) e[RL + 4 + i] = __shfl_down_sync(0xffffffffu, a[i], 1);
+__host__ __device__ constexpr bool uses_term(bool pair, int pos) {
+    for (int c = 0; c < 4; ++c) {
+        int x = c - RL;
+        const int hi = c + RR;
+        if (x & 1) { if (!pair && x == pos) return true; ++x; }
+        for (; x + 1 <= hi; x += 2) if (pair && x == pos) return true;
+        if (x == hi && !pair && x == pos) return true;
+    }
+    return false;
+}
+
+// Paired window sums of 4 consecutive positions 0..3 (position 0 is even in absolute terms).
+// s[i] = element at position i-4 (i = 0..11), p[i] = pair sum starting at position 2i-4 (i = 0..5);
+// only the entries uses_term() asks for have to be filled in.
+template <int RL, int RR>
+__device__ __forceinline__ void paired_sums(const float (&s)[12], const float (&p)[6], float (&out)[4]) {
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
-        float s = e[c];
+        int x = c - RL;
+        const int hi = c + RR;
+        float acc = 0.f;
+        bool first = true;
+        if (x & 1) { acc = s[x + 4]; first = false; ++x; }
 #pragma unroll
-        for (int d = 1; d <= RL + RR; ++d) s = __fadd_rn(s, e[c + d]);
-        h[c] = s;
+        for (int i = 0; i < 4; ++i) {                 // at most 4 pairs in a window of <= 9
+            if (x + 1 <= hi) {
+                acc = first ? p[(x + 4) / 2] : __fadd_rn(acc, p[(x + 4) / 2]);
+                first = false;
+                x += 2;
+            }
+        }
+        if (x == hi) acc = first ? s[x + 4] : __fadd_rn(acc, s[x + 4]);
+        out[c] = acc;
     }
+}
+
+// row sums of one patch row: the lane's 4 columns; neighbours' elements / pair sums by shuffle
+template <int RL, int RR>
+__device__ __forceinline__ void row_sums(const float (&a)[4], float (&h)[4]) {
+    float s[12], p[6];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) s[4 + i] = a[i];
+    constexpr bool need_p0 = uses_term<RL, RR>(true, 0) || uses_term<RL, RR>(true, -4) || uses_term<RL, RR>(true, 4);
+    constexpr bool need_p2 = uses_term<RL, RR>(true, 2) || uses_term<RL, RR>(true, -2) || uses_term<RL, RR>(true, 6);
+    if (need_p0) p[2] = __fadd_rn(a[0], a[1]);
+    if (need_p2) p[3] = __fadd_rn(a[2], a[3]);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        if (uses_term<RL, RR>(false, i - 4)) s[i] = __shfl_up_sync(0xffffffffu, a[i], 1);       // left lane's element i
+        if (uses_term<RL, RR>(false, i + 4)) s[8 + i] = __shfl_down_sync(0xffffffffu, a[i], 1);   // right lane's element i
+    }
+    if (uses_term<RL, RR>(true, -4)) p[0] = __shfl_up_sync(0xffffffffu, p[2], 1);
+    if (uses_term<RL, RR>(true, -2)) p[1] = __shfl_up_sync(0xffffffffu, p[3], 1);
+    if (uses_term<RL, RR>(true, 4)) p[4] = __shfl_down_sync(0xffffffffu, p[2], 1);
+    if (uses_term<RL, RR>(true, 6)) p[5] = __shfl_down_sync(0xffffffffu, p[3], 1);
+    paired_sums<RL, RR>(s, p, h);
 }
 
 template <int RL, int RR, int R, int NWARP, bool MASKED>
@@ -346,21 +405,52 @@ __device__ __forceinline__ void tile_sweeps(float (&u)[R][4], float (&v)[R][4],
                 *reinterpret_cast<float4*>(exv + o) = make_float4(hv[j][0], hv[j][1], hv[j][2], hv[j][3]);
             }
         }
-        // one patch row: box sum from the row sums of rows j-RL..j+RR, then the update
+        static_assert(R == 4, "the shared column pairs below are (0,1) and (2,3)");
+        float qu[2][4], qv[2][4];                      // shared pair sums of the patch's own rows
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            qu[0][c] = __fadd_rn(hu[0][c], hu[1][c]); qv[0][c] = __fadd_rn(hv[0][c], hv[1][c]);
+            qu[1][c] = __fadd_rn(hu[2][c], hu[3][c]); qv[1][c] = __fadd_rn(hv[2][c], hv[3][c]);
+        }
+        // one patch row: paired box sum down the column from the row sums of rows j-RL..j+RR (the
+        // patch's first row is an even image row), then the update
+        auto column_term = [&](const float (&hh)[R][4], const float (&ab)[RL > 0 ? RL : 1][4],
+                               const float (&be)[RR > 0 ? RR : 1][4], int i, int c) {
+            return i < 0 ? ab[i + RL][c] : (i >= R ? be[i - R][c] : hh[i][c]);
+        };
         auto update_row = [&](int j, const float (&au)[RL > 0 ? RL : 1][4], const float (&av)[RL > 0 ? RL : 1][4],
                               const float (&bu)[RR > 0 ? RR : 1][4], const float (&bv)[RR > 0 ? RR : 1][4]) {
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
                 float su = 0.f, sv = 0.f;
+                bool first = true;
+                int i = j - RL;
+                const int hi = j + RR;
+                if (i & 1) {
+                    su = column_term(hu, au, bu, i, c); sv = column_term(hv, av, bv, i, c);
+                    first = false; ++i;
+                }
 #pragma unroll
-                for (int d = -RL; d <= RR; ++d) {
-                    const int i = j + d;  // patch-relative row of this tap
-                    float tu, tv;
-                    if (i < 0) { tu = au[i + RL][c]; tv = av[i + RL][c]; }
-                    else if (i >= R) { tu = bu[i - R][c]; tv = bv[i - R][c]; }
-                    else { tu = hu[i][c]; tv = hv[i][c]; }
-                    su = (d == -RL) ? tu : __fadd_rn(su, tu);
-                    sv = (d == -RL) ? tv : __fadd_rn(sv, tv);
+                for (int q = 0; q < 4; ++q) {
+                    if (i + 1 <= hi) {
+                        // pair (i, i+1), i even: inside the patch it is one of the two shared sums
+                        float pu, pv;
+                        if (i == 0) { pu = qu[0][c]; pv = qv[0][c]; }
+                        else if (i == 2) { pu = qu[1][c]; pv = qv[1][c]; }
+                        else {
+                            pu = __fadd_rn(column_term(hu, au, bu, i, c), column_term(hu, au, bu, i + 1, c));
+                            pv = __fadd_rn(column_term(hv, av, bv, i, c), column_term(hv, av, bv, i + 1, c));
+                        }
+                        su = first ? pu : __fadd_rn(su, pu);
+                        sv = first ? pv : __fadd_rn(sv, pv);
+                        first = false;
+                        i += 2;
+                    }
+                }
+                if (i == hi) {
+                    const float tu = column_term(hu, au, bu, i, c), tv = column_term(hv, av, bv, i, c);
+                    su = first ? tu : __fadd_rn(su, tu);
+                    sv = first ? tv : __fadd_rn(sv, tv);
                 }
                 float nu, nv;
                 hs_update(su, sv, kf, ix[j][c], iy[j][c], it[j][c], iv[j][c], nu, nv);

@@ -35,7 +35,7 @@ class Solver:
     """One hs_ctx: fixed geometry and parameters, reusable across frame pairs."""
 
     def __init__(self, width, height, window_size, max_iterations, alpha, batch=1, device=-1,
-                 temporal_k=0, flags=0, out_rows=None, stream=None):
+                 temporal_k=0, flags=0, out_rows=None, stream=None, global_row0=0):
         self._lib = H.load_library()
         cfg = H.HsConfig()
         cfg.struct_size = C.sizeof(H.HsConfig)
@@ -46,6 +46,7 @@ class Solver:
         if out_rows is not None:
             cfg.out_row_begin, cfg.out_row_end = int(out_rows[0]), int(out_rows[1])
         cfg.stream = stream
+        cfg.global_row0 = int(global_row0)
         self._ctx = C.c_void_p()
         rc = self._lib.hs_create(C.byref(cfg), C.byref(self._ctx))
         if rc != H.HS_OK:

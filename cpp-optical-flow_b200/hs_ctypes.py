@@ -25,7 +25,7 @@ class HsConfig(C.Structure):
                 ("window_size", C.c_int32), ("max_iterations", C.c_int32), ("alpha", C.c_double),
                 ("batch", C.c_int32), ("device", C.c_int32), ("temporal_k", C.c_int32),
                 ("flags", C.c_uint32), ("out_row_begin", C.c_int32), ("out_row_end", C.c_int32),
-                ("stream", C.c_void_p)]
+                ("stream", C.c_void_p), ("global_row0", C.c_int32)]
 
 
 class HsTiming(C.Structure):

@@ -156,7 +156,8 @@ class DeviceSlab:
         self.comm_stream = torch.cuda.Stream(device=self._device)   # halo exchange, overlapped with interior rows
         flags = (H.FLAG_TOP_IS_SEAM if geom.top_seam else 0) | (H.FLAG_BOTTOM_IS_SEAM if geom.bottom_seam else 0)
         self.solver = Solver(geom.width, geom.rows, geom.window, iterations, alpha, device=device,
-                             temporal_k=geom.k, flags=flags, out_rows=geom.out_rows, stream=self.stream.cuda_stream)
+                             temporal_k=geom.k, flags=flags, out_rows=geom.out_rows, stream=self.stream.cuda_stream,
+                             global_row0=geom.b0)
         self.k = self.solver.timing().temporal_k
         if self.k != geom.k:
             raise ValueError(f"library chose k={self.k}, slab plan was made for k={geom.k}")

@@ -81,6 +81,7 @@ typedef struct hs_config {
     int32_t out_row_begin;
     int32_t out_row_end;
     void* stream;           /* cudaStream_t to run on; NULL = a private non-blocking stream       */
+    int32_t global_row0;    /* row slabs: image row of this context's buffer row 0 (default 0)    */
 } hs_config;
 
 typedef struct hs_ctx hs_ctx;
