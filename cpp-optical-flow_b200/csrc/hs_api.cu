@@ -65,6 +65,16 @@ struct hs_ctx {
     float* d_inv = nullptr;
     void* d_out = nullptr;
     size_t out_bytes = 0;
+    uint8_t* d_bgr = nullptr;    // staging for hs_solve_bgr: two 8UC3 frames
+    // streaming front-end (hs_video_*): frame ring, copy stream, double-buffered output staging
+    uint8_t* d_ring[3] = {nullptr, nullptr, nullptr};   // [0], [1] are the context's own prev/next
+    void* d_vout[2] = {nullptr, nullptr};
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev_up = nullptr, ev_k1[3] = {nullptr, nullptr, nullptr}, ev_solved[2] = {nullptr, nullptr};
+    int vid_frames = 0;          // frames pushed so far
+    int vid_pending = -1;        // pair solved (or being solved) whose flow was not handed out yet
+    int vid_dtype = -1;
+    size_t bgr_pitch = 0;
 
     CUtensorMap tm_u[2], tm_v[2], tm_cpk, tm_inv;
     int kernel_id = 0;  // 0 generic, 1 fused tile
@@ -242,6 +252,7 @@ int do_upload(hs_ctx* c, const uint8_t* prev, size_t ps, size_t pis, const uint8
         return fail(c, HS_ERR_INVALID_ARG, "row stride smaller than width");
     if (c->B > 1 && (pis < ps * c->frows || nis < ns * c->frows))
         return fail(c, HS_ERR_INVALID_ARG, "image stride smaller than one image");
+    if (c->d_ring[0]) { c->d_prev = c->d_ring[0]; c->d_next = c->d_ring[1]; }   // leave streaming mode
     for (int b = 0; b < c->B; ++b) {
         HS_CUDA(c, cudaMemcpy2DAsync(c->d_prev + (size_t)b * c->fimg, c->fpitch, prev + (size_t)b * pis, ps,
                                      c->W, c->frows, cudaMemcpyHostToDevice, c->stream));
@@ -341,9 +352,14 @@ void destroy_impl(hs_ctx* c) {
     {
         DevGuard g(c->dev);
         if (c->stream) cudaStreamSynchronize(c->stream);
-        cudaFree(c->d_prev); cudaFree(c->d_next);
+        cudaFree(c->d_ring[0] ? c->d_ring[0] : c->d_prev); cudaFree(c->d_ring[1] ? c->d_ring[1] : c->d_next);
+        cudaFree(c->d_ring[2]); cudaFree(c->d_vout[0]); cudaFree(c->d_vout[1]);
+        if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+        if (c->ev_up) cudaEventDestroy(c->ev_up);
+        for (auto& e : c->ev_k1) if (e) cudaEventDestroy(e);
+        for (auto& e : c->ev_solved) if (e) cudaEventDestroy(e);
         for (int i = 0; i < 2; ++i) { cudaFree(c->d_u[i]); cudaFree(c->d_v[i]); }
-        cudaFree(c->d_cpk); cudaFree(c->d_inv); cudaFree(c->d_done); cudaFree(c->d_out);
+        cudaFree(c->d_cpk); cudaFree(c->d_inv); cudaFree(c->d_done); cudaFree(c->d_bgr); cudaFree(c->d_out);
         for (auto& e : c->ev) if (e) cudaEventDestroy(e);
         if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
     }
@@ -597,6 +613,47 @@ int hs_solve(hs_ctx* c, const uint8_t* prev, size_t ps, size_t pis, const uint8_
     return HS_OK;
 }
 
+int hs_solve_bgr(hs_ctx* c, const uint8_t* prev, size_t ps, const uint8_t* next, size_t ns,
+                 void* u, size_t us, void* v, size_t vs, int dt) {
+    if (!c) return HS_ERR_INVALID_ARG;
+    if (c->B != 1 || c->top_seam || c->bot_seam)
+        return fail(c, HS_ERR_UNSUPPORTED, "hs_solve_bgr needs a whole-image, batch == 1 context");
+    if (!prev || !next) return fail(c, HS_ERR_INVALID_ARG, "null frame pointer");
+    if (ps < (size_t)c->W * 3 || ns < (size_t)c->W * 3) return fail(c, HS_ERR_INVALID_ARG, "row stride smaller than 3*width");
+    DevGuard g(c->dev);
+    c->timing.launches = 0;
+    if (!c->d_bgr) {
+        c->bgr_pitch = (size_t)round_up(c->W * 3, 128);
+        HS_CUDA(c, cudaMalloc(&c->d_bgr, c->bgr_pitch * c->H * 2));
+    }
+    int rc;
+    HS_CUDA(c, cudaEventRecord(c->ev[0], c->stream));
+    uint8_t* d0 = c->d_bgr;
+    uint8_t* d1 = c->d_bgr + c->bgr_pitch * c->H;
+    HS_CUDA(c, cudaMemcpy2DAsync(d0, c->bgr_pitch, prev, ps, (size_t)c->W * 3, c->H, cudaMemcpyHostToDevice, c->stream));
+    HS_CUDA(c, cudaMemcpy2DAsync(d1, c->bgr_pitch, next, ns, (size_t)c->W * 3, c->H, cudaMemcpyHostToDevice, c->stream));
+    HS_CUDA(c, cudaEventRecord(c->ev[1], c->stream));
+    dim3 grid(((c->W + 3) / 4 + 255) / 256, c->H);
+    hs::k_bgr2gray<<<grid, 256, 0, c->stream>>>(d0, c->bgr_pitch, c->d_prev, c->fpitch, c->W, c->H);   // main.cpp:11-26
+    hs::k_bgr2gray<<<grid, 256, 0, c->stream>>>(d1, c->bgr_pitch, c->d_next, c->fpitch, c->W, c->H);
+    HS_CUDA(c, cudaGetLastError());
+    c->timing.launches += 2;
+    c->uploaded = true;
+    if ((rc = do_prepare(c))) return rc;
+    HS_CUDA(c, cudaEventRecord(c->ev[2], c->stream));
+    if ((rc = do_iterate(c, c->T))) return rc;
+    HS_CUDA(c, cudaEventRecord(c->ev[3], c->stream));
+    if ((rc = do_download(c, u, us, 0, v, vs, 0, dt))) return rc;
+    HS_CUDA(c, cudaEventRecord(c->ev[4], c->stream));
+    HS_CUDA(c, cudaStreamSynchronize(c->stream));
+    c->timing.h2d_ms = ev_ms(c->ev[0], c->ev[1]);
+    c->timing.prepare_ms = ev_ms(c->ev[1], c->ev[2]);
+    c->timing.iterate_ms = ev_ms(c->ev[2], c->ev[3]);
+    c->timing.d2h_ms = ev_ms(c->ev[3], c->ev[4]);
+    c->timing.total_ms = ev_ms(c->ev[0], c->ev[4]);
+    return HS_OK;
+}
+
 int hs_gradients(hs_ctx* c, const uint8_t* prev, size_t ps, const uint8_t* next, size_t ns, void* gx, void* gy,
                  void* gt, size_t os, int dt) {
     if (!c) return HS_ERR_INVALID_ARG;
@@ -678,3 +735,114 @@ int hs_host_free(void* ptr) {
 }
 
 }  // extern "C"
+
+// ---- streaming front-end -----------------------------------------------------------------------
+namespace {
+
+int video_setup(hs_ctx* c, int dt) {
+    if (c->B != 1 || c->top_seam || c->bot_seam)
+        return fail(c, HS_ERR_UNSUPPORTED, "hs_video_* needs a whole-image, batch == 1 context");
+    if (dt != HS_F32 && dt != HS_F64) return fail(c, HS_ERR_INVALID_ARG, "bad out_dtype");
+    if (!c->copy_stream) {
+        HS_CUDA(c, cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+        HS_CUDA(c, cudaEventCreateWithFlags(&c->ev_up, cudaEventDisableTiming));
+        for (auto& e : c->ev_k1) HS_CUDA(c, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        for (auto& e : c->ev_solved) HS_CUDA(c, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        c->d_ring[0] = c->d_prev;
+        c->d_ring[1] = c->d_next;
+        HS_CUDA(c, cudaMalloc(&c->d_ring[2], c->fimg));
+        for (auto& o : c->d_vout) HS_CUDA(c, cudaMalloc(&o, (size_t)c->plane * 2 * sizeof(double)));
+    }
+    if (c->vid_dtype >= 0 && c->vid_dtype != dt && (c->vid_pending >= 0))
+        return fail(c, HS_ERR_INVALID_ARG, "out_dtype changed while a pair is pending");
+    c->vid_dtype = dt;
+    return HS_OK;
+}
+
+// copy the flow of pair p from its staging slot to the host and wait for exactly that copy
+int video_fetch(hs_ctx* c, int p, void* u, size_t us, void* v, size_t vs) {
+    if (!u || !v) return fail(c, HS_ERR_INVALID_ARG, "null output pointer");
+    const size_t es = c->vid_dtype == HS_F64 ? 8 : 4;
+    if (us < c->W * es || vs < c->W * es) return fail(c, HS_ERR_INVALID_ARG, "output row stride smaller than a row");
+    const char* src = static_cast<const char*>(c->d_vout[p & 1]);
+    HS_CUDA(c, cudaStreamWaitEvent(c->copy_stream, c->ev_solved[p & 1], 0));
+    HS_CUDA(c, cudaMemcpy2DAsync(u, us, src, (size_t)c->pitch * es, c->W * es, c->H, cudaMemcpyDeviceToHost, c->copy_stream));
+    HS_CUDA(c, cudaMemcpy2DAsync(v, vs, src + (size_t)c->plane * es, (size_t)c->pitch * es, c->W * es, c->H,
+                                 cudaMemcpyDeviceToHost, c->copy_stream));
+    HS_CUDA(c, cudaStreamSynchronize(c->copy_stream));
+    return HS_OK;
+}
+
+}  // namespace
+
+extern "C" int hs_video_reset(hs_ctx* c) {
+    if (!c) return HS_ERR_INVALID_ARG;
+    DevGuard g(c->dev);
+    HS_CUDA(c, cudaStreamSynchronize(c->stream));
+    if (c->copy_stream) HS_CUDA(c, cudaStreamSynchronize(c->copy_stream));
+    c->vid_frames = 0;
+    c->vid_pending = -1;
+    c->vid_dtype = -1;
+    return HS_OK;
+}
+
+extern "C" int hs_video_push(hs_ctx* c, const uint8_t* frame, size_t stride, void* u, size_t us, void* v, size_t vs,
+                             int dt, int* pair_index) {
+    if (!c || !pair_index) return HS_ERR_INVALID_ARG;
+    *pair_index = -1;
+    if (!frame) return fail(c, HS_ERR_INVALID_ARG, "null frame pointer");
+    if (stride < (size_t)c->W) return fail(c, HS_ERR_INVALID_ARG, "row stride smaller than width");
+    DevGuard g(c->dev);
+    int rc = video_setup(c, dt);
+    if (rc) return rc;
+    const int n = c->vid_frames;
+    // 1. upload frame n into ring slot n % 3 (last read by the gradient kernel of pair n-3)
+    if (n >= 3) HS_CUDA(c, cudaStreamWaitEvent(c->copy_stream, c->ev_k1[(n - 3) % 3], 0));
+    HS_CUDA(c, cudaMemcpy2DAsync(c->d_ring[n % 3], c->fpitch, frame, stride, c->W, c->H, cudaMemcpyHostToDevice,
+                                 c->copy_stream));
+    HS_CUDA(c, cudaEventRecord(c->ev_up, c->copy_stream));
+    c->vid_frames = n + 1;
+    if (n == 0) return HS_OK;
+    // 2. queue the solve of pair p = (n-1, n) on the compute stream
+    const int p = n - 1;
+    const int prev_pending = c->vid_pending;
+    HS_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_up, 0));
+    c->d_prev = c->d_ring[(n - 1) % 3];
+    c->d_next = c->d_ring[n % 3];
+    c->uploaded = true;
+    c->timing.launches = 0;
+    if ((rc = do_prepare(c))) return rc;
+    HS_CUDA(c, cudaEventRecord(c->ev_k1[p % 3], c->stream));
+    if ((rc = do_iterate(c, c->T))) return rc;
+    const long long npx = c->plane;
+    if (dt == HS_F64) {
+        double* o = static_cast<double*>(c->d_vout[p & 1]);
+        hs::k_widen<<<148 * 8, 256, 0, c->stream>>>(c->d_u[c->cur], c->d_v[c->cur], o, o + npx, npx);
+        HS_CUDA(c, cudaGetLastError());
+        c->timing.launches += 1;
+    } else {
+        float* o = static_cast<float*>(c->d_vout[p & 1]);
+        HS_CUDA(c, cudaMemcpyAsync(o, c->d_u[c->cur], npx * sizeof(float), cudaMemcpyDeviceToDevice, c->stream));
+        HS_CUDA(c, cudaMemcpyAsync(o + npx, c->d_v[c->cur], npx * sizeof(float), cudaMemcpyDeviceToDevice, c->stream));
+    }
+    HS_CUDA(c, cudaEventRecord(c->ev_solved[p & 1], c->stream));
+    c->vid_pending = p;
+    // 3. hand out the previous pair while this one is being solved
+    if (prev_pending >= 0) {
+        if ((rc = video_fetch(c, prev_pending, u, us, v, vs))) return rc;
+        *pair_index = prev_pending;
+    }
+    return HS_OK;
+}
+
+extern "C" int hs_video_flush(hs_ctx* c, void* u, size_t us, void* v, size_t vs, int* pair_index) {
+    if (!c || !pair_index) return HS_ERR_INVALID_ARG;
+    *pair_index = -1;
+    if (c->vid_pending < 0) return HS_OK;
+    DevGuard g(c->dev);
+    int rc = video_fetch(c, c->vid_pending, u, us, v, vs);
+    if (rc) return rc;
+    *pair_index = c->vid_pending;
+    c->vid_pending = -1;
+    return HS_OK;
+}

@@ -117,6 +117,36 @@ k_grad_coeff(const uint8_t* __restrict__ prev, const uint8_t* __restrict__ next,
 }
 
 // ------------------------------------------------------------------------------------------
+// K0: the caller's preprocess() on the device (HornSchunckOF/main.cpp:11-26): 8UC3 BGR -> 8UC1 with
+// OpenCV's 15-bit fixed-point luma, Y = (3735 B + 19235 G + 9798 R + 2^14) >> 15 (bit-exact with
+// cv::cvtColor(COLOR_BGR2GRAY)).  4 pixels (12 bytes in, 4 out) per thread.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_bgr2gray(const uint8_t* __restrict__ bgr, size_t bgr_pitch, uint8_t* __restrict__ gray, size_t gray_pitch,
+           int W, int H) {
+    const int x0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    const int y = blockIdx.y;
+    if (x0 >= W || y >= H) return;
+    const uint8_t* src = bgr + (size_t)y * bgr_pitch + (size_t)x0 * 3;
+    uint8_t* dst = gray + (size_t)y * gray_pitch + x0;
+    uint32_t out = 0;
+    if (x0 + 4 <= W) {
+        const uint32_t* s32 = reinterpret_cast<const uint32_t*>(src);   // 12 bytes, 4-byte aligned (pitch % 4 == 0)
+        const uint32_t w0 = s32[0], w1 = s32[1], w2 = s32[2];
+        const uint32_t b[4] = {w0 & 255u, (w0 >> 24) & 255u, (w1 >> 16) & 255u, (w2 >> 8) & 255u};
+        const uint32_t gch[4] = {(w0 >> 8) & 255u, w1 & 255u, (w1 >> 24) & 255u, (w2 >> 16) & 255u};
+        const uint32_t r[4] = {(w0 >> 16) & 255u, (w1 >> 8) & 255u, w2 & 255u, (w2 >> 24) & 255u};
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+            out |= ((3735u * b[i] + 19235u * gch[i] + 9798u * r[i] + 16384u) >> 15) << (8 * i);
+        *reinterpret_cast<uint32_t*>(dst) = out;                          // gray pitch is a multiple of 128
+    } else {
+        for (int i = 0; x0 + i < W; ++i)
+            dst[i] = (uint8_t)((3735u * src[3 * i] + 19235u * src[3 * i + 1] + 9798u * src[3 * i + 2] + 16384u) >> 15);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // the per-pixel update, shared by K2 and K3 (hornSchunck.cpp:63-73)
 // ------------------------------------------------------------------------------------------
 __device__ __forceinline__ void hs_update(float su, float sv, float kf, float ix, float iy,
@@ -227,7 +257,7 @@ __device__ __forceinline__ unsigned long long global_ns() {
 }
 // Every device-side wait is bounded: a protocol bug must end in a trapped kernel, never in a GPU
 // that spins forever (a hung kernel cannot be killed from the host).
-constexpr unsigned long long WAIT_LIMIT_NS = 4000000000ull;   // 4 s
+constexpr unsigned long long WAIT_LIMIT_NS = 20000000000ull;   // 20 s
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     uint32_t done;
     unsigned long long t0 = 0;

@@ -118,6 +118,29 @@ class Solver:
                                        u.ctypes.data, rs, ims, v.ctypes.data, rs, ims, dt))
         return u, v
 
+    def solve_bgr(self, prev_bgr, next_bgr, out_dtype=np.float64):
+        """preprocess() + getFlow (main.cpp:11-26,84,98): 8UC3 BGR frames in, BGR2GRAY on the device."""
+        p = np.asarray(prev_bgr)
+        n = np.asarray(next_bgr)
+        if p.ndim != 3 or p.shape[2] != 3 or p.dtype != np.uint8 or p.shape != n.shape or n.dtype != np.uint8:
+            raise ValueError("solve_bgr expects two uint8 H x W x 3 frames of the same size")
+        if p.shape[:2] != (self.height, self.width):
+            raise ValueError(f"frames are {p.shape[:2]}, context was created for {(self.height, self.width)}")
+
+        def aligned(a):     # the device conversion reads rows as 32-bit words
+            a = np.ascontiguousarray(a)
+            if a.strides[0] % 4 or a.ctypes.data % 4:
+                buf = np.zeros((a.shape[0], (a.shape[1] * 3 + 3) // 4 * 4), np.uint8)
+                buf[:, :a.shape[1] * 3] = a.reshape(a.shape[0], -1)
+                return buf, buf.strides[0]
+            return a, a.strides[0]
+
+        (p, ps), (n, ns) = aligned(p), aligned(n)
+        u, v, dt = self._outputs(out_dtype)
+        self._check(self._lib.hs_solve_bgr(self._ctx, p.ctypes.data, ps, n.ctypes.data, ns,
+                                           u.ctypes.data, u.strides[0], v.ctypes.data, v.strides[0], dt))
+        return u, v
+
     def gradients(self, prev, nxt, out_dtype=np.float64):
         """getGradients (hornSchunck.cpp:19-41): -> (gradX, gradY, gradT)."""
         p, n, ps, ns, _, _ = self._frames(prev, nxt)
@@ -164,6 +187,30 @@ class Solver:
 
     def download_raw(self, u_ptr, v_ptr, row_stride, img_stride, dt):
         self._check(self._lib.hs_download(self._ctx, u_ptr, row_stride, img_stride, v_ptr, row_stride, img_stride, dt))
+
+    # -- streaming front-end (frame sequences) --------------------------------------------------
+    def video_reset(self):
+        self._check(self._lib.hs_video_reset(self._ctx))
+
+    def video_push(self, frame, out_dtype=np.float64):
+        """Push the next frame of a sequence.  Returns (pair_index, u, v) for the pair that became
+        available (one pair behind the frame just pushed), or None while the pipeline fills."""
+        f = _as_u8_image(frame, "frame")
+        if f.shape != (self.height, self.width):
+            raise ValueError(f"frame is {f.shape}, context was created for {(self.height, self.width)}")
+        u, v, dt = self._outputs(out_dtype)
+        idx = C.c_int(-1)
+        self._check(self._lib.hs_video_push(self._ctx, f.ctypes.data, f.strides[0], u.ctypes.data, u.strides[0],
+                                            v.ctypes.data, v.strides[0], dt, C.byref(idx)))
+        self._keep = f
+        return None if idx.value < 0 else (idx.value, u, v)
+
+    def video_flush(self, out_dtype=np.float64):
+        u, v, _ = self._outputs(out_dtype)
+        idx = C.c_int(-1)
+        self._check(self._lib.hs_video_flush(self._ctx, u.ctypes.data, u.strides[0], v.ctypes.data, v.strides[0],
+                                             C.byref(idx)))
+        return None if idx.value < 0 else (idx.value, u, v)
 
     def device_view(self) -> H.HsDeviceView:
         view = H.HsDeviceView()

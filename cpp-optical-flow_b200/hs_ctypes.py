@@ -15,9 +15,9 @@ STATUS_NAMES = {0: "HS_OK", 1: "HS_ERR_INVALID_ARG", 2: "HS_ERR_CUDA", 3: "HS_ER
                 4: "HS_ERR_UNSUPPORTED", 5: "HS_ERR_STATE"}
 
 # every extern "C" symbol include/hs.h declares (tests check the library exports all of them)
-SYMBOLS = ["hs_create", "hs_destroy", "hs_solve", "hs_gradients", "hs_upload", "hs_prepare",
+SYMBOLS = ["hs_create", "hs_destroy", "hs_solve", "hs_solve_bgr", "hs_gradients", "hs_upload", "hs_prepare",
            "hs_iterate", "hs_iterate_rows", "hs_solve_device", "hs_download", "hs_sync", "hs_get_device_view",
-           "hs_get_timing", "hs_last_error", "hs_version", "hs_host_alloc", "hs_host_free"]
+           "hs_video_push", "hs_video_flush", "hs_video_reset", "hs_get_timing", "hs_last_error", "hs_version", "hs_host_alloc", "hs_host_free"]
 
 
 class HsConfig(C.Structure):
@@ -71,6 +71,7 @@ def load_library(path: str | None = None):
     lib.hs_destroy.restype = None
     lib.hs_solve.argtypes = [vp, vp, sz, sz, vp, sz, sz, vp, sz, sz, vp, sz, sz, i32]
     lib.hs_gradients.argtypes = [vp, vp, sz, vp, sz, vp, vp, vp, sz, i32]
+    lib.hs_solve_bgr.argtypes = [vp, vp, sz, vp, sz, vp, sz, vp, sz, i32]
     lib.hs_upload.argtypes = [vp, vp, sz, sz, vp, sz, sz]
     lib.hs_prepare.argtypes = [vp]
     lib.hs_iterate.argtypes = [vp, i32]
@@ -78,6 +79,9 @@ def load_library(path: str | None = None):
     lib.hs_solve_device.argtypes = [vp]
     lib.hs_download.argtypes = [vp, vp, sz, sz, vp, sz, sz, i32]
     lib.hs_sync.argtypes = [vp]
+    lib.hs_video_push.argtypes = [vp, vp, sz, vp, sz, vp, sz, i32, C.POINTER(C.c_int)]
+    lib.hs_video_flush.argtypes = [vp, vp, sz, vp, sz, C.POINTER(C.c_int)]
+    lib.hs_video_reset.argtypes = [vp]
     lib.hs_get_device_view.argtypes = [vp, C.POINTER(HsDeviceView)]
     lib.hs_get_timing.argtypes = [vp, C.POINTER(HsTiming)]
     lib.hs_last_error.argtypes = [vp]

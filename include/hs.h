@@ -132,6 +132,14 @@ int hs_solve(hs_ctx* ctx,
              void* v, size_t v_row_stride, size_t v_image_stride,
              int out_dtype);
 
+/* preprocess() + getFlow in one call (HornSchunckOF/main.cpp:11-26,84 then :98): prev/next are 8UC3
+ * BGR frames (row stride >= 3*width bytes, a multiple of 4); the BGR2GRAY conversion runs on the
+ * device with OpenCV's fixed-point luma (bit-exact with cv::cvtColor).  batch == 1 contexts. */
+int hs_solve_bgr(hs_ctx* ctx,
+                 const uint8_t* prev_bgr, size_t prev_row_stride,
+                 const uint8_t* next_bgr, size_t next_row_stride,
+                 void* u, size_t u_row_stride, void* v, size_t v_row_stride, int out_dtype);
+
 /* hornSchunck::getGradients  hornSchunck.cpp:19-41.  gx/gy/gt: host outputs of out_dtype, all
  * with the same row stride (batch == 1 contexts only). */
 int hs_gradients(hs_ctx* ctx,
@@ -158,6 +166,18 @@ int hs_download(hs_ctx* ctx,                                  /* device u,v -> h
                 void* v, size_t v_row_stride, size_t v_image_stride, int out_dtype);
 int hs_sync(hs_ctx* ctx);                                     /* wait for the context's stream   */
 int hs_get_device_view(hs_ctx* ctx, hs_device_view* out);
+
+/* ---- streaming front-end for frame sequences (the .mp4 branch, HornSchunckOF/main.cpp:53-59) -------
+ * Every frame is uploaded once and serves as `next` of one pair and `prev` of the following one.
+ * hs_video_push(frame n) queues the solve of pair (n-1, n) and, while that runs, returns the flow
+ * of the PREVIOUS pair (n-2, n-1) in u, v: *pair_index = n-2, or -1 when no flow is due yet (then
+ * u, v are not touched).  Upload, solve and download of consecutive pairs overlap on two streams.
+ * hs_video_flush returns the last pair; hs_video_reset starts a new sequence.  out_dtype must stay
+ * the same within a sequence.  batch == 1 contexts; use pinned host buffers for full overlap. */
+int hs_video_push(hs_ctx* ctx, const uint8_t* frame, size_t row_stride,
+                  void* u, size_t u_row_stride, void* v, size_t v_row_stride, int out_dtype, int* pair_index);
+int hs_video_flush(hs_ctx* ctx, void* u, size_t u_row_stride, void* v, size_t v_row_stride, int* pair_index);
+int hs_video_reset(hs_ctx* ctx);
 
 /* ---- introspection --------------------------------------------------------------------------- */
 int hs_get_timing(const hs_ctx* ctx, hs_timing* out);

@@ -133,6 +133,51 @@ def test_alpha_zero_nan_pattern_matches_reference(pkg, oracle):
     assert np.allclose(u[m], ou[m], atol=1e-4) and np.allclose(v[m], ov[m], atol=1e-4)
 
 
+@pytest.mark.parametrize("shape", [(33, 47), (64, 96), (120, 161), (375, 1242)])
+def test_solve_bgr_equals_preprocess_then_solve(pkg, oracle, shape):
+    """main.cpp's preprocess() (BGR2GRAY) fused in front of the path, on the device."""
+    import cv2
+    rng = np.random.default_rng(shape[1])
+    a = rng.integers(0, 256, shape + (3,), dtype=np.uint8)
+    b = np.clip(a.astype(int) + rng.integers(-12, 13, a.shape), 0, 255).astype(np.uint8)
+    ga, gb = cv2.cvtColor(a, cv2.COLOR_BGR2GRAY), cv2.cvtColor(b, cv2.COLOR_BGR2GRAY)
+    assert np.array_equal(ga, oracle.bgr2gray(a))
+    with pkg.Solver(shape[1], shape[0], 3, 9, 1.0) as s:
+        u, v = s.solve_bgr(a, b)
+        gu, gv = s.solve(ga, gb)
+        u1, _ = pkg.Solver(shape[1], shape[0], 3, 1, 1.0).solve_bgr(a, b)   # one sweep: u = -Ix*It*inv, gray-exact
+        g1, _ = pkg.Solver(shape[1], shape[0], 3, 1, 1.0).solve(ga, gb)
+    assert np.array_equal(u, gu) and np.array_equal(v, gv) and np.array_equal(u1, g1)
+    *_, ou, ov = oracle.np_flow(ga, gb, 3, 9, 1.0)
+    assert_flow_close(u, v, ou, ov)
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_video_stream_equals_pairwise_solves(pkg, dtype):
+    """frame sequence front-end (main.cpp:53-59); flows arrive one pair late, in order."""
+    from cpp_optical_flow_b200 import synth
+    frames = [synth.frame_pair(150, 260, seed=3, shift=(0.3 * i, -0.2 * i))[1] for i in range(6)]
+    with pkg.Solver(260, 150, 3, 25, 1.0) as ref:
+        want = [ref.solve(frames[i], frames[i + 1], dtype) for i in range(5)]
+    got = {}
+    with pkg.Solver(260, 150, 3, 25, 1.0) as s:
+        for rep in range(2):                                  # a second sequence after reset
+            s.video_reset()
+            got.clear()
+            order = []
+            for f in frames:
+                r = s.video_push(f, dtype)
+                if r is not None:
+                    got[r[0]] = (r[1], r[2]); order.append(r[0])
+            r = s.video_flush(dtype)
+            got[r[0]] = (r[1], r[2]); order.append(r[0])
+            assert order == [0, 1, 2, 3, 4] and s.video_flush(dtype) is None
+            for i in range(5):
+                assert np.array_equal(got[i][0], want[i][0]) and np.array_equal(got[i][1], want[i][1])
+        u, v = s.solve(frames[0], frames[1], dtype)           # the plain path still works afterwards
+        assert np.array_equal(u, want[0][0])
+
+
 # ---------------------------------------------------------------- invariances (bit-exact)
 @pytest.mark.parametrize("w,k", [(3, 1), (3, 2), (3, 3), (3, 4), (3, 7), (3, 12), (5, 1), (5, 2), (5, 3), (5, 5),
                                  (2, 4), (2, 9), (4, 2), (4, 3)])
