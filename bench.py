@@ -38,7 +38,7 @@ WORKLOADS = {
     # name: (height, width, default iterations, BASELINE.json config it restates)
     "1080p": (1080, 1920, 1000, "configs[1]: synthetic textured 1920x1080 pair, alpha=1, 1000 Jacobi iterations"),
     "4k": (2160, 3840, 2000, "configs[2]: synthetic 3840x2160 pair, 2000 iterations"),
-    "kitti": (375, 1242, 100, "configs[0]: bundled 1242x375 pair size, w=5, 100 iterations (synthetic texture)"),
+    "kitti": (375, 1242, 100, "configs[0]: the bundled 1242x375 pair 000050_10/11 (tests/golden fixture), w=5, 100 iterations"),
     "slab16k": (16384, 16384, 5000, "configs[4]: one 16384x16384 pair, 5000 iterations, row slabs + halo exchange"),
 }
 ALGO_BYTES_PER_PIXEL_ITER = 32.0       # u,v read 8 + Ix,Iy,It,inv read 16 + u,v write 8 (fp32)
@@ -144,6 +144,10 @@ def run_reference(args, rank, world):
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import cv2
     import hs_oracle
+    if args.workload == "kitti":
+        g = os.path.join(ROOT, "tests", "golden")
+        prev = cv2.imread(os.path.join(g, "kitti_000050_10_gray.png"), cv2.IMREAD_UNCHANGED)
+        nxt = cv2.imread(os.path.join(g, "kitti_000050_11_gray.png"), cv2.IMREAD_UNCHANGED)
     iters = args.ref_iters
     for _ in range(args.warmup):
         hs_oracle.cv_flow(prev, nxt, args.window, max(1, iters // 4), 1.0)
@@ -155,7 +159,8 @@ def run_reference(args, rank, world):
     sample = f"{W}x{H} frame pair, {iters} of {args.iters or T_default} sweeps per step (throughput is per sweep)"
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "Mpixel-iter/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "bundled frame pair of the reference" if args.workload == "kitti" else "synthetic",
             "config": {"workload": f"{args.workload}: {cfgname}", "window": args.window, "alpha": 1.0,
                        "iterations": args.iters or T_default},
             "cpu_baseline": {"value": val, "unit": "Mpixel-iter/s", "cores": cv2.getNumThreads(), "kind": "port",
@@ -191,7 +196,15 @@ def run_ours(args, rank, local_rank, world):
     window = args.window
     dev = torch.device("cuda", local_rank)
     stream = torch.cuda.Stream(device=dev)
-    prev, nxt = synth.video_pair(rank, H, W) if world > 1 else synth.frame_pair(H, W)
+    data = "synthetic"
+    if args.workload == "kitti":
+        import cv2
+        g = os.path.join(ROOT, "tests", "golden")
+        prev = cv2.imread(os.path.join(g, "kitti_000050_10_gray.png"), cv2.IMREAD_UNCHANGED)
+        nxt = cv2.imread(os.path.join(g, "kitti_000050_11_gray.png"), cv2.IMREAD_UNCHANGED)
+        data = "bundled frame pair of the reference (HornSchunckOF/img/leftimage/000050_10/11.png, gray)"
+    else:
+        prev, nxt = synth.video_pair(rank, H, W) if world > 1 else synth.frame_pair(H, W)
 
     solver = pkg.Solver(W, H, window, T, 1.0, device=local_rank, temporal_k=args.k, stream=stream.cuda_stream)
     solver.upload(prev, nxt)
@@ -314,7 +327,7 @@ def run_ours(args, rank, local_rank, world):
 
     line = {"metric": METRIC, "value": value, "unit": "Mpixel-iter/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": float(np.mean(step_ms)), "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": data,
             "config": {"workload": f"{args.workload}: {cfgname}", "window": window, "alpha": 1.0, "iterations": T,
                        "pairs_per_rank_per_step": 1, "parallelism": f"independent pairs x{world}" if world > 1 else "1 gpu",
                        "l2": "512 MiB memset before every step (cold L2 at step start; events exclude it)",
@@ -344,13 +357,16 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="1080p", choices=sorted(WORKLOADS))
-    ap.add_argument("--window", type=int, default=3, help="windowSize (3 = the north star's 3x3; main.cpp uses 5)")
+    ap.add_argument("--window", type=int, default=0,
+                    help="windowSize; default 3 (the north star's 3x3), 5 for --workload kitti (main.cpp:94)")
     ap.add_argument("--iters", type=int, default=0, help="override the workload's iteration count")
     ap.add_argument("--k", type=int, default=0, help="fused sweeps per launch (0 = library default)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline sample")
     ap.add_argument("--ref-iters", type=int, default=16, help="--impl reference: sweeps per step (bounded sample)")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
+    if args.window <= 0:
+        args.window = 5 if args.workload == "kitti" else 3
     rank, local_rank, world = dist_env()
     if args.impl == "reference":
         return run_reference(args, rank, world)

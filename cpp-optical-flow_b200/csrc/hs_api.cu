@@ -688,6 +688,28 @@ int hs_gradients(hs_ctx* c, const uint8_t* prev, size_t ps, const uint8_t* next,
     return HS_OK;
 }
 
+int hs_sample_grid(hs_ctx* c, int delta, double* u, double* v, int* ny_out, int* nx_out) {
+    if (!c || delta < 1) return HS_ERR_INVALID_ARG;
+    if (c->B != 1) return fail(c, HS_ERR_UNSUPPORTED, "hs_sample_grid needs a batch == 1 context");
+    const int rows = c->oy1 - c->oy0;
+    const int ny = (rows + delta - 1) / delta, nx = (c->W + delta - 1) / delta;
+    if (ny_out) *ny_out = ny;
+    if (nx_out) *nx_out = nx;
+    if (!u || !v) return HS_OK;                           // size query
+    DevGuard g(c->dev);
+    const size_t n = (size_t)ny * nx;
+    int rc = ensure_out(c, n * 2 * sizeof(double));
+    if (rc) return rc;
+    double* o = static_cast<double*>(c->d_out);
+    hs::k_sample_grid<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(c->d_u[c->cur], c->d_v[c->cur], o, o + n,
+                                                                       c->pitch, c->oy0, delta, ny, nx);
+    HS_CUDA(c, cudaGetLastError());
+    HS_CUDA(c, cudaMemcpyAsync(u, o, n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    HS_CUDA(c, cudaMemcpyAsync(v, o + n, n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    HS_CUDA(c, cudaStreamSynchronize(c->stream));
+    return HS_OK;
+}
+
 int hs_get_device_view(hs_ctx* c, hs_device_view* o) {
     if (!c || !o) return HS_ERR_INVALID_ARG;
     o->prev = c->d_prev; o->next = c->d_next;

@@ -852,6 +852,19 @@ k_widen(const float* __restrict__ a, const float* __restrict__ b2, double* __res
     }
 }
 
+// Flow samples on the plot grid: plotFlow::plotBresenhamLine reads u, v only at rows/columns that
+// are multiples of `delta` (plotFlow.cpp:70-75); this gathers just those (row-major grid order).
+__global__ void __launch_bounds__(256)
+k_sample_grid(const float* __restrict__ u, const float* __restrict__ v, double* __restrict__ ou,
+              double* __restrict__ ov, int pitch, int row0, int delta, int ny, int nx) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= ny * nx) return;
+    const int gy = i / nx, gx = i - gy * nx;
+    const size_t o = (size_t)(row0 + gy * delta) * pitch + (size_t)gx * delta;
+    ou[i] = (double)u[o];
+    ov[i] = (double)v[o];
+}
+
 template <typename T>
 __global__ void __launch_bounds__(256)
 k_unpack_grad(const uint32_t* __restrict__ cpk, T* __restrict__ gx, T* __restrict__ gy,

@@ -188,6 +188,16 @@ class Solver:
     def download_raw(self, u_ptr, v_ptr, row_stride, img_stride, dt):
         self._check(self._lib.hs_download(self._ctx, u_ptr, row_stride, img_stride, v_ptr, row_stride, img_stride, dt))
 
+    def sample_grid(self, delta=20):
+        """u, v of the current device-resident flow at the plot grid (plotFlow.cpp:70-75): rows and
+        columns that are multiples of `delta`.  -> two float64 arrays [ceil(H/delta), ceil(W/delta)]."""
+        ny, nx = C.c_int(), C.c_int()
+        self._check(self._lib.hs_sample_grid(self._ctx, int(delta), None, None, C.byref(ny), C.byref(nx)))
+        u = np.empty((ny.value, nx.value), np.float64)
+        v = np.empty((ny.value, nx.value), np.float64)
+        self._check(self._lib.hs_sample_grid(self._ctx, int(delta), u.ctypes.data, v.ctypes.data, None, None))
+        return u, v
+
     # -- streaming front-end (frame sequences) --------------------------------------------------
     def video_reset(self):
         self._check(self._lib.hs_video_reset(self._ctx))

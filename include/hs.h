@@ -165,6 +165,12 @@ int hs_download(hs_ctx* ctx,                                  /* device u,v -> h
                 void* u, size_t u_row_stride, size_t u_image_stride,
                 void* v, size_t v_row_stride, size_t v_image_stride, int out_dtype);
 int hs_sync(hs_ctx* ctx);                                     /* wait for the context's stream   */
+/* Only what the reference's plot consumes: plotFlow::plotBresenhamLine (plotFlow.cpp:68-88) reads
+ * u, v at rows/columns that are multiples of `delta` (20 in main.cpp:104).  Gathers those samples of
+ * the current device-resident flow as doubles, row-major ny x nx, ny = ceil(rows/delta),
+ * nx = ceil(width/delta) (1 197 values instead of 7.5 MB for the bundled 1242x375 pair).
+ * Pass u == v == NULL to query ny / nx only. */
+int hs_sample_grid(hs_ctx* ctx, int delta, double* u, double* v, int* ny, int* nx);
 int hs_get_device_view(hs_ctx* ctx, hs_device_view* out);
 
 /* ---- streaming front-end for frame sequences (the .mp4 branch, HornSchunckOF/main.cpp:53-59) -------

@@ -178,6 +178,25 @@ def test_video_stream_equals_pairwise_solves(pkg, dtype):
         assert np.array_equal(u, want[0][0])
 
 
+def test_grid_sampler_feeds_the_reference_plot(pkg, oracle, kitti):
+    """plotFlow reads only every 20th row/column (plotFlow.cpp:70-75).  The device-side
+    sampler returns exactly those values, and they draw the reference's golden plot."""
+    a, b = kitti("000050")
+    with pkg.Solver(a.shape[1], a.shape[0], 5, 100, 1.0) as s:
+        s.upload(a, b); s.solve_device()
+        gu, gv = s.sample_grid(20)
+        u, v = s.download(np.float64)
+    assert gu.shape == (19, 63)
+    assert np.array_equal(gu, u[::20, ::20]) and np.array_equal(gv, v[::20, ::20])
+    # scatter the samples into otherwise empty fields: the plot only looks at the grid
+    su = np.zeros_like(u); sv = np.zeros_like(v)
+    su[::20, ::20] = gu; sv[::20, ::20] = gv
+    gold = np.load(os.path.join(GOLDEN, "plot_000050.npz"))
+    img = oracle.plot_bresenham(np.full(a.shape + (3,), 7, np.uint8), su, sv, 20, 20.0, 5)
+    yx = gold["yx"].astype(np.int64)
+    assert int((img[yx[:, 0], yx[:, 1]] != gold["bgr"]).any(axis=1).sum()) <= 20
+
+
 # ---------------------------------------------------------------- invariances (bit-exact)
 @pytest.mark.parametrize("w,k", [(3, 1), (3, 2), (3, 3), (3, 4), (3, 7), (3, 12), (5, 1), (5, 2), (5, 3), (5, 5),
                                  (2, 4), (2, 9), (4, 2), (4, 3)])
