@@ -13,6 +13,7 @@ echo "== bench (1080p w=3, then w=5, 4k)"
 python bench.py --steps 10 --warmup 3 > gpurun_out/${TAG}_bench_1080p_w3.json 2> gpurun_out/${TAG}_bench.err; tail -c 3000 gpurun_out/${TAG}_bench_1080p_w3.json
 python bench.py --steps 5 --warmup 3 --window 5 --no-cpu > gpurun_out/${TAG}_bench_1080p_w5.json 2>> gpurun_out/${TAG}_bench.err
 python bench.py --steps 3 --warmup 3 --workload 4k --no-cpu > gpurun_out/${TAG}_bench_4k_w3.json 2>> gpurun_out/${TAG}_bench.err
+python bench.py --steps 10 --warmup 3 --workload kitti --no-cpu > gpurun_out/${TAG}_bench_kitti_w5.json 2>> gpurun_out/${TAG}_bench.err
 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/${TAG}_bench_reference.json 2>> gpurun_out/${TAG}_bench.err
 tail -5 gpurun_out/${TAG}_bench.err
 echo "== ncu launch list"
