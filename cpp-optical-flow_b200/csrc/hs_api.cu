@@ -206,6 +206,13 @@ struct Tile {
                                   c->tm_inv, c->d_u[a], c->d_v[a], c->d_u[b], c->d_v[b], c->d_done, g,
                                   tg, kf);
     }
+    static size_t tiles_for(const hs_ctx* c, int k) {          // tiles of one phase (row 0 even)
+        const int vx = TS::SX - round_up(RL * k, 4) - round_up(RR * k, 4);
+        const int hyt = RL * k + ((c->oy0 + c->grow0 + RL * k) & 1);
+        const int vy = (TS::SY - hyt - RR * k) & ~1;
+        if (vx <= 0 || vy <= 0) return 0;
+        return (size_t)((c->W + vx - 1) / vx) * ((c->oy1 - c->oy0 + vy - 1) / vy) * c->B;
+    }
     static size_t max_tiles(const hs_ctx* c) {                 // upper bound over all k (k = 1 tiles are the largest)
         size_t best = 0;
         for (int k = 1; k <= max_k(); ++k) {
@@ -507,6 +514,13 @@ int hs_create(const hs_config* cfg_in, hs_ctx** out) {
         cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
         c->multi_phase = coop && !c->top_seam && !c->bot_seam && !(cfg.flags & HS_FLAG_SINGLE_PHASE) &&
                          env_int("HS_SINGLE_PHASE", 0) == 0;
+        // The dataflow launch pays off when a phase is at least two rounds of tiles per SM: then a
+        // tile's inputs were published about a round before its turn.  With fewer tiles every
+        // phase is one dependent round and the publish/poll latency is exposed; plain launches
+        // chained by PDL are faster there (measured on the 1242x375 pair: 377 vs 275 Gpix-it/s).
+        size_t tiles_k = 0;
+        tile_dispatch(c->RL, c->RR, [&](auto t) { tiles_k = decltype(t)::tiles_for(c, c->k); });
+        if (tiles_k < (size_t)2 * c->num_sms && env_int("HS_MULTI_PHASE", 0) == 0) c->multi_phase = false;
     }
     c->timing.temporal_k = c->k;
     c->timing.kernel_id = c->kernel_id;
