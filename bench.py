@@ -117,21 +117,40 @@ class ClockSampler:
 # ---------------------------------------------------------------------------------------------
 # reference arm / cpu_baseline: the reference's own CPU algorithm on the box's host cores
 # ---------------------------------------------------------------------------------------------
-def cpu_reference_rate(prev, nxt, window, alpha, seconds_budget):
-    """Time the cv2 restatement of hornSchunck.cpp on a bounded number of sweeps of this workload."""
+REF_BINARY = os.path.join(ROOT, "oracle", "_ref", "hs_ref")   # built by `make -C oracle ref` iff OpenCV C++ exists
+
+
+def reference_solve_seconds(prev, nxt, window, iters, alpha):
+    """Wall seconds of ONE getFlow of the reference's CPU path on these frames, and what ran:
+    ("reference", threads, description) when the unmodified hornSchunck.cpp could be compiled here
+    (oracle/_ref/hs_ref), else ("port", ...) = the line-by-line cv2 restatement."""
+    if os.path.exists(REF_BINARY):
+        import tempfile
+        with tempfile.TemporaryDirectory() as d:
+            pa, pb = os.path.join(d, "a.raw"), os.path.join(d, "b.raw")
+            np.ascontiguousarray(prev).tofile(pa); np.ascontiguousarray(nxt).tofile(pb)
+            out = subprocess.run([REF_BINARY, pa, pb, str(prev.shape[0]), str(prev.shape[1]), str(window), str(iters),
+                                  repr(float(alpha))], capture_output=True, text=True, check=True).stdout
+        fields = dict(kv.split("=") for kv in out.split())
+        return float(fields["seconds"]), "reference", int(fields["threads"]), "HornSchunckOF/hornSchunck.cpp compiled with g++ -O3 (oracle/_ref/hs_ref)"
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import cv2
     import hs_oracle
-    threads = cv2.getNumThreads()
-    t0 = time.perf_counter()
-    hs_oracle.cv_flow(prev, nxt, window, 2, alpha)          # includes the gradient stage, like a solve
-    per_iter = max((time.perf_counter() - t0) / 2.0, 1e-4)
-    iters = int(min(max(seconds_budget / per_iter, 4), 400))
     t0 = time.perf_counter()
     hs_oracle.cv_flow(prev, nxt, window, iters, alpha)
-    dt = time.perf_counter() - t0
+    return (time.perf_counter() - t0, "port", cv2.getNumThreads(),
+            f"oracle/hs_oracle.py::cv_flow = hornSchunck.cpp:19-75 through cv2 {cv2.__version__} "
+            "(C++ OpenCV absent: hornSchunck.cpp not compilable here)")
+
+
+def cpu_reference_rate(prev, nxt, window, alpha, seconds_budget):
+    """Time the reference's CPU path on a bounded number of sweeps of this workload."""
+    t2, kind, threads, what = reference_solve_seconds(prev, nxt, window, 2, alpha)   # incl. the gradient stage
+    per_iter = max(t2 / 2.0, 1e-4)
+    iters = int(min(max(seconds_budget / per_iter, 4), 400))
+    dt, kind, threads, what = reference_solve_seconds(prev, nxt, window, iters, alpha)
     rate = prev.shape[0] * prev.shape[1] * iters / dt / 1e6
-    return rate, threads, iters, dt, cv2.__version__
+    return rate, threads, iters, dt, kind, what
 
 
 def run_reference(args, rank, world):
@@ -151,11 +170,11 @@ def run_reference(args, rank, world):
         nxt = cv2.imread(os.path.join(g, "kitti_000050_11_gray.png"), cv2.IMREAD_UNCHANGED)
     iters = args.ref_iters
     for _ in range(args.warmup):
-        hs_oracle.cv_flow(prev, nxt, args.window, max(1, iters // 4), 1.0)
-    t0 = time.perf_counter()
+        reference_solve_seconds(prev, nxt, args.window, max(1, iters // 4), 1.0)
+    dt, kind, threads, what = 0.0, "port", 1, ""
     for _ in range(args.steps):
-        hs_oracle.cv_flow(prev, nxt, args.window, iters, 1.0)
-    dt = time.perf_counter() - t0
+        t, kind, threads, what = reference_solve_seconds(prev, nxt, args.window, iters, 1.0)
+        dt += t
     val = H * W * iters * args.steps / dt / 1e6
     sample = f"{W}x{H} frame pair, {iters} of {args.iters or T_default} sweeps per step (throughput is per sweep)"
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "Mpixel-iter/s", "n_gpus": args.gpus,
@@ -164,10 +183,8 @@ def run_reference(args, rank, world):
             "data": "bundled frame pair of the reference" if args.workload == "kitti" else "synthetic",
             "config": {"workload": f"{args.workload}: {cfgname}", "window": args.window, "alpha": 1.0,
                        "iterations": args.iters or T_default},
-            "cpu_baseline": {"value": val, "unit": "Mpixel-iter/s", "cores": cv2.getNumThreads(), "kind": "port",
-                             "sample": sample,
-                             "what": "oracle/hs_oracle.py::cv_flow = hornSchunck.cpp:19-75 through cv2 "
-                                     f"{cv2.__version__} (C++ OpenCV absent: hornSchunck.cpp not compilable here)"},
+            "cpu_baseline": {"value": val, "unit": "Mpixel-iter/s", "cores": threads, "kind": kind,
+                             "sample": sample, "what": what},
             "e2e": {"value": val, "unit": "Mpixel-iter/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
@@ -325,9 +342,9 @@ def run_ours(args, rank, local_rank, world):
 
     cpu = None
     if world == 1 and not args.no_cpu:
-        rate, threads, its, dt, cvv = cpu_reference_rate(prev, nxt, window, 1.0, args.cpu_seconds)
-        cpu = {"value": rate, "unit": "Mpixel-iter/s", "cores": threads, "kind": "port",
-               "sample": f"same {W}x{H} pair, {its} of {T} sweeps ({dt:.1f} s), cv2 {cvv} restatement of hornSchunck.cpp"}
+        rate, threads, its, dt, kind, what = cpu_reference_rate(prev, nxt, window, 1.0, args.cpu_seconds)
+        cpu = {"value": rate, "unit": "Mpixel-iter/s", "cores": threads, "kind": kind,
+               "sample": f"same {W}x{H} pair, {its} of {T} sweeps ({dt:.1f} s)", "what": what}
 
     line = {"metric": METRIC, "value": value, "unit": "Mpixel-iter/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": float(np.mean(step_ms)), "higher_is_better": True,
