@@ -52,6 +52,20 @@ def test_ctypes_structs_match_the_header_layout(pkg, tmp_path):
     assert got == want, (got, want)
 
 
+def test_header_is_plain_c_and_links(pkg, tmp_path):
+    """include/hs.h compiles as pedantic C99; a C program links against the library and gets the
+    documented behaviour (argument errors; HS_ERR_CUDA without a GPU, a solve with one)."""
+    import subprocess
+    pkg.load_library()
+    libdir = os.path.join(ROOT, "cpp-optical-flow_b200")
+    exe = str(tmp_path / "abi_smoke")
+    subprocess.run(["/usr/bin/gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-pedantic",
+                    "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "tests", "c", "abi_smoke.c"),
+                    "-o", exe, "-L", libdir, "-l:libhs_b200.so", f"-Wl,-rpath,{libdir}"], check=True)
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 0, (r.returncode, r.stdout, r.stderr)
+
+
 def test_create_rejects_bad_arguments_before_touching_cuda(pkg):
     from cpp_optical_flow_b200 import hs_ctypes as H
     lib = pkg.load_library()
