@@ -227,7 +227,8 @@ def run_ours(args, rank, local_rank, world):
     else:
         prev, nxt = synth.video_pair(rank, H, W) if world > 1 else synth.frame_pair(H, W)
 
-    solver = pkg.Solver(W, H, window, T, 1.0, device=local_rank, temporal_k=args.k, stream=stream.cuda_stream)
+    solver = pkg.Solver(W, H, window, T, 1.0, device=local_rank, temporal_k=args.k, stream=stream.cuda_stream,
+                        flags=HC.FLAG_TEXTBOOK if args.textbook else 0)
     solver.upload(prev, nxt)
     solver.sync()
     flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)      # > 126 MB L2
@@ -341,7 +342,7 @@ def run_ours(args, rank, local_rank, world):
                         "trip is why frac can exceed 1"}
 
     cpu = None
-    if world == 1 and not args.no_cpu:
+    if world == 1 and not args.no_cpu and not args.textbook:
         rate, threads, its, dt, kind, what = cpu_reference_rate(prev, nxt, window, 1.0, args.cpu_seconds)
         cpu = {"value": rate, "unit": "Mpixel-iter/s", "cores": threads, "kind": kind,
                "sample": f"same {W}x{H} pair, {its} of {T} sweeps ({dt:.1f} s)", "what": what}
@@ -352,7 +353,8 @@ def run_ours(args, rank, local_rank, world):
             "config": {"workload": f"{args.workload}: {cfgname}", "window": window, "alpha": 1.0, "iterations": T,
                        "pairs_per_rank_per_step": 1, "parallelism": f"independent pairs x{world}" if world > 1 else "1 gpu",
                        "l2": "512 MiB memset before every step (cold L2 at step start; events exclude it)",
-                       "temporal_k": tm.temporal_k},
+                       "temporal_k": tm.temporal_k,
+                       **({"mode": "textbook Horn-Schunck (HS_FLAG_TEXTBOOK): NOT the reference's arithmetic"} if args.textbook else {})},
             "roofline": roofline,
             "e2e": {"value": e2e_value, "unit": "Mpixel-iter/s", "h2d_bytes_per_step": 2 * H * W,
                     "d2h_bytes_per_step": 2 * H * W * 8, "steps": e2e_steps,
@@ -468,6 +470,8 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline sample")
     ap.add_argument("--ref-iters", type=int, default=16, help="--impl reference: sweeps per step (bounded sample)")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--textbook", action="store_true",
+                    help="non-parity extra: cube gradients + weighted 3x3 average (HS_FLAG_TEXTBOOK); no CPU baseline")
     args = ap.parse_args()
     if args.window <= 0:
         args.window = 5 if args.workload == "kitti" else 3

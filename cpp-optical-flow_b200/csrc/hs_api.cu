@@ -50,6 +50,7 @@ struct hs_ctx {
     long long plane = 0;
     int oy0 = 0, oy1 = 0, grow0 = 0;
     bool top_seam = false, bot_seam = false;
+    bool textbook = false;       // HS_FLAG_TEXTBOOK: cube gradients + weighted 3x3 average (non-parity extra)
 
     int frows = 0, frow0 = 0;
     size_t fpitch = 0, fimg = 0;
@@ -149,10 +150,10 @@ int env_int(const char* name, int dflt) {
     return (s && *s) ? atoi(s) : dflt;
 }
 
-template <int RL, int RR>
+template <int RL, int RR, bool TB = false>
 struct Tile {
     using TS = hs::TileShape<RL, RR, TILE_R, TILE_NWARP>;
-    static auto kernel() { return hs::k_jacobi_tile<RL, RR, TILE_R, TILE_NWARP>; }
+    static auto kernel() { return hs::k_jacobi_tile<RL, RR, TILE_R, TILE_NWARP, TB>; }
     static cudaError_t configure() {
         return cudaFuncSetAttribute(kernel(), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TS::SMEM);
     }
@@ -204,7 +205,7 @@ struct Tile {
         g.oy1 = row1;
         return cudaLaunchKernelEx(&cfg, kernel(), c->tm_u[a], c->tm_v[a], c->tm_u[b], c->tm_v[b], c->tm_cpk,
                                   c->tm_inv, c->d_u[a], c->d_v[a], c->d_u[b], c->d_v[b], c->d_done, g,
-                                  tg, kf);
+                                  tg, kf, (float)(c->alpha * c->alpha));
     }
     static size_t tiles_for(const hs_ctx* c, int k) {          // tiles of one phase (row 0 even)
         const int vx = TS::SX - round_up(RL * k, 4) - round_up(RR * k, 4);
@@ -227,7 +228,9 @@ struct Tile {
 
 // dispatch on (RL, RR) = (anchor, w - 1 - anchor); returns false when no fused kernel exists
 template <typename F>
-bool tile_dispatch(int RL, int RR, F&& f) {
+bool tile_dispatch(const hs_ctx* c, F&& f) {
+    const int RL = c->RL, RR = c->RR;
+    if (c->textbook) { f(Tile<1, 1, true>{}); return true; }    // weighted 3x3 average
     if (RL == 0 && RR == 1) { f(Tile<0, 1>{}); return true; }   // w = 2
     if (RL == 1 && RR == 1) { f(Tile<1, 1>{}); return true; }   // w = 3
     if (RL == 1 && RR == 2) { f(Tile<1, 2>{}); return true; }   // w = 4
@@ -282,8 +285,12 @@ int do_prepare(hs_ctx* c) {
     dim3 block(32, 8);
     dim3 grid((c->pitch / 4 + 31) / 32, (c->H + 7) / 8, c->B);
     const float a2 = (float)(c->alpha * c->alpha);
-    hs::k_grad_coeff<<<grid, block, 0, c->stream>>>(c->d_prev, c->d_next, c->fpitch, c->fimg, c->frows,
-                                                    c->frow0, c->d_cpk, c->d_inv, c->geom(), a2);
+    if (c->textbook)
+        hs::k_grad_coeff_tb<<<grid, block, 0, c->stream>>>(c->d_prev, c->d_next, c->fpitch, c->fimg, c->frows,
+                                                           c->frow0, c->d_cpk, c->d_inv, c->geom());
+    else
+        hs::k_grad_coeff<<<grid, block, 0, c->stream>>>(c->d_prev, c->d_next, c->fpitch, c->fimg, c->frows,
+                                                        c->frow0, c->d_cpk, c->d_inv, c->geom(), a2);
     HS_CUDA(c, cudaGetLastError());
     c->timing.launches += 1;
     c->prepared = true;
@@ -301,15 +308,20 @@ int do_iterate(hs_ctx* c, int iters) {
             // everything in one multi-phase launch, unless the caller must refresh halos between
             // fused launches (row slabs) or asked for per-launch behaviour
             step = c->multi_phase ? left : std::min(c->k, left);
-            tile_dispatch(c->RL, c->RR, [&](auto t) { e = decltype(t)::launch(c, std::min(c->k, step), step, c->oy0, c->oy1); });
+            tile_dispatch(c, [&](auto t) { e = decltype(t)::launch(c, std::min(c->k, step), step, c->oy0, c->oy1); });
             if (e == cudaSuccess && (((step + c->k - 1) / c->k) & 1)) c->cur ^= 1;
         } else {
             dim3 block(32, 8);
             dim3 grid((c->W + 31) / 32, (c->oy1 - c->oy0 + 7) / 8, c->B);
             const float kf = 1.0f / (float)(c->w * c->w);
-            hs::k_jacobi_generic<<<grid, block, 0, c->stream>>>(c->d_u[c->cur], c->d_v[c->cur], c->d_u[c->cur ^ 1],
-                                                                c->d_v[c->cur ^ 1], c->d_cpk, c->d_inv,
-                                                                c->geom(), c->w, c->a, kf);
+            if (c->textbook)
+                hs::k_jacobi_generic_tb<<<grid, block, 0, c->stream>>>(c->d_u[c->cur], c->d_v[c->cur], c->d_u[c->cur ^ 1],
+                                                                       c->d_v[c->cur ^ 1], c->d_cpk, c->d_inv, c->geom(),
+                                                                       (float)(c->alpha * c->alpha));
+            else
+                hs::k_jacobi_generic<<<grid, block, 0, c->stream>>>(c->d_u[c->cur], c->d_v[c->cur], c->d_u[c->cur ^ 1],
+                                                                    c->d_v[c->cur ^ 1], c->d_cpk, c->d_inv,
+                                                                    c->geom(), c->w, c->a, kf);
             e = cudaGetLastError();
             c->cur ^= 1;
         }
@@ -418,6 +430,7 @@ int hs_create(const hs_config* cfg_in, hs_ctx** out) {
     c->oy0 = cfg.out_row_begin; c->oy1 = cfg.out_row_end;
     if (c->oy0 == 0 && c->oy1 == 0) c->oy1 = c->H;
     c->grow0 = cfg.global_row0;
+    c->textbook = (cfg.flags & HS_FLAG_TEXTBOOK) != 0;
     c->top_seam = cfg.flags & HS_FLAG_TOP_IS_SEAM;
     c->bot_seam = cfg.flags & HS_FLAG_BOTTOM_IS_SEAM;
     c->pitch = round_up(c->W, 32);
@@ -428,6 +441,8 @@ int hs_create(const hs_config* cfg_in, hs_ctx** out) {
     c->fimg = c->fpitch * c->frows;
 
     auto bail = [&](int code) { g_create_err = c->err; destroy_impl(c); return code; };
+    if (c->textbook && c->w != 3)
+        return bail(fail(c, HS_ERR_INVALID_ARG, "HS_FLAG_TEXTBOOK is a 3x3 weighted average: window_size must be 3"));
     if (c->oy0 < 0 || c->oy1 > c->H || c->oy0 >= c->oy1)
         return bail(fail(c, HS_ERR_INVALID_ARG, "out rows [%d,%d) not inside [0,%d)", c->oy0, c->oy1, c->H));
 
@@ -473,7 +488,7 @@ int hs_create(const hs_config* cfg_in, hs_ctx** out) {
     bool have_tile = false;
     int kmax = 1;
     if (!force_generic)
-        have_tile = tile_dispatch(c->RL, c->RR, [&](auto t) {
+        have_tile = tile_dispatch(c, [&](auto t) {
             using TT = decltype(t);
             kmax = TT::max_k();
             e = TT::configure();
@@ -507,7 +522,7 @@ int hs_create(const hs_config* cfg_in, hs_ctx** out) {
                          c->RL * c->k, c->RR * c->k, c->k, c->oy0, c->H - c->oy1));
     if (c->kernel_id == 1) {
         size_t cap = 0;
-        tile_dispatch(c->RL, c->RR, [&](auto t) { cap = decltype(t)::max_tiles(c); });
+        tile_dispatch(c, [&](auto t) { cap = decltype(t)::max_tiles(c); });
         HS_CREATE_CUDA(cudaMalloc(&c->d_done, std::max<size_t>(cap, 1) * sizeof(int)));
         c->done_cap = cap;
         int coop = 0;
@@ -519,7 +534,7 @@ int hs_create(const hs_config* cfg_in, hs_ctx** out) {
         // phase is one dependent round and the publish/poll latency is exposed; plain launches
         // chained by PDL are faster there (measured on the 1242x375 pair: 377 vs 275 Gpix-it/s).
         size_t tiles_k = 0;
-        tile_dispatch(c->RL, c->RR, [&](auto t) { tiles_k = decltype(t)::tiles_for(c, c->k); });
+        tile_dispatch(c, [&](auto t) { tiles_k = decltype(t)::tiles_for(c, c->k); });
         if (tiles_k < (size_t)2 * c->num_sms && env_int("HS_MULTI_PHASE", 0) == 0) c->multi_phase = false;
     }
     c->timing.temporal_k = c->k;
@@ -559,7 +574,7 @@ int hs_iterate_rows(hs_ctx* c, int sweeps, int row_begin, int row_end, int flip)
         return fail(c, HS_ERR_INVALID_ARG, "rows [%d,%d) not inside the buffer rows [0,%d)", row_begin, row_end, c->H);
     DevGuard g(c->dev);
     cudaError_t e = cudaSuccess;
-    tile_dispatch(c->RL, c->RR, [&](auto t) { e = decltype(t)::launch(c, sweeps, sweeps, row_begin, row_end); });
+    tile_dispatch(c, [&](auto t) { e = decltype(t)::launch(c, sweeps, sweeps, row_begin, row_end); });
     if (e != cudaSuccess) return fail(c, HS_ERR_CUDA, "sweep launch failed: %s", cudaGetErrorString(e));
     c->timing.launches += 1;
     if (flip) c->cur ^= 1;
@@ -686,10 +701,12 @@ int hs_gradients(hs_ctx* c, const uint8_t* prev, size_t ps, const uint8_t* next,
     char* o = static_cast<char*>(c->d_out);
     if (dt == HS_F64) {
         double* d = reinterpret_cast<double*>(o);
-        hs::k_unpack_grad<double><<<148 * 8, 256, 0, c->stream>>>(c->d_cpk, d, d + n, d + 2 * n, n);
+        if (c->textbook) hs::k_unpack_grad_tb<double><<<148 * 8, 256, 0, c->stream>>>(c->d_cpk, c->d_inv, d, d + n, d + 2 * n, n);
+        else hs::k_unpack_grad<double><<<148 * 8, 256, 0, c->stream>>>(c->d_cpk, d, d + n, d + 2 * n, n);
     } else {
         float* d = reinterpret_cast<float*>(o);
-        hs::k_unpack_grad<float><<<148 * 8, 256, 0, c->stream>>>(c->d_cpk, d, d + n, d + 2 * n, n);
+        if (c->textbook) hs::k_unpack_grad_tb<float><<<148 * 8, 256, 0, c->stream>>>(c->d_cpk, c->d_inv, d, d + n, d + 2 * n, n);
+        else hs::k_unpack_grad<float><<<148 * 8, 256, 0, c->stream>>>(c->d_cpk, d, d + n, d + 2 * n, n);
     }
     HS_CUDA(c, cudaGetLastError());
     c->timing.launches += 1;

@@ -149,14 +149,104 @@ k_bgr2gray(const uint8_t* __restrict__ bgr, size_t bgr_pitch, uint8_t* __restric
 // ------------------------------------------------------------------------------------------
 // the per-pixel update, shared by K2 and K3 (hornSchunck.cpp:63-73)
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ void hs_update(float su, float sv, float kf, float ix, float iy,
-                                          float it, float inv, float& un, float& vn) {
-    const float ub = __fmul_rn(su, kf);
-    const float vb = __fmul_rn(sv, kf);
+__device__ __forceinline__ void hs_update_bar(float ub, float vb, float ix, float iy, float it, float inv,
+                                              float& un, float& vn) {
     const float t = __fmaf_rn(ix, ub, __fmaf_rn(iy, vb, it));
     const float c = __fmul_rn(t, inv);
     un = __fmaf_rn(-ix, c, ub);
     vn = __fmaf_rn(-iy, c, vb);
+}
+__device__ __forceinline__ void hs_update(float su, float sv, float kf, float ix, float iy,
+                                          float it, float inv, float& un, float& vn) {
+    hs_update_bar(__fmul_rn(su, kf), __fmul_rn(sv, kf), ix, iy, it, inv, un, vn);
+}
+
+// ---- "textbook" Horn-Schunck mode (HS_FLAG_TEXTBOOK; SURVEY 8f row 4, NOT a parity item: the
+// reference does not compute this, BASELINE.json's prose does) --------------------------------------
+//   gradients: Horn & Schunck's 2x2x2 cube, Ix = 1/4 [sum over y,t in {0,1} of I(x+1,.)-I(x,.)] etc.,
+//              replicated at the right/bottom border; 4*Ix, 4*Iy, 4*It are exact integers <= 1020
+//   average:   ubar = 1/6 (N,S,E,W) + 1/12 (diagonals) = 1/12 (s121 x s121)(u) - 1/3 u, zeros outside
+//   canonical: h(x) = fma(2, t[x], t[x-1] + t[x+1]);  V(y) = fma(2, h[y], h[y-1] + h[y+1]);
+//              ubar = fma(V, 1/12, u * (-1/3))
+// Coefficients: `cpk` holds 4*Ix, 4*Iy (11-bit biased fields), the second plane holds It as float
+// (It is a multiple of 1/4), and inv is recomputed per tile (33 bits do not fit one word).
+#define HS_TB_W12 0.083333336f
+#define HS_TB_W3 (-0.33333334f)
+__device__ __forceinline__ void unpack_coef_tb(uint32_t w, float& ix, float& iy) {
+    float i4, j4, unused;
+    unpack_coef(w, i4, j4, unused);
+    ix = __fmul_rn(i4, 0.25f);
+    iy = __fmul_rn(j4, 0.25f);
+}
+__device__ __forceinline__ float hs_inv(float ix, float iy, float alpha2) {
+    return __fdiv_rn(1.0f, __fadd_rn(alpha2, __fmaf_rn(ix, ix, __fmul_rn(iy, iy))));
+}
+__device__ __forceinline__ float tb_bar(float V, float centre) {
+    return __fmaf_rn(V, HS_TB_W12, __fmul_rn(centre, HS_TB_W3));
+}
+
+// K1 for the textbook mode
+__global__ void __launch_bounds__(256)
+k_grad_coeff_tb(const uint8_t* __restrict__ prev, const uint8_t* __restrict__ next,
+                size_t fpitch, size_t fimg, int frows, int frow0,
+                uint32_t* __restrict__ cpk, float* __restrict__ itp, Geom g) {
+    const int x0 = (blockIdx.x * 32 + threadIdx.x) * 4;
+    const int y = blockIdx.y * 8 + threadIdx.y;
+    const int b = blockIdx.z;
+    if (x0 >= g.pitch || y >= g.H) return;
+    const uint8_t* P = prev + (size_t)b * fimg;
+    const uint8_t* N = next + (size_t)b * fimg;
+    const int fy = y + frow0;
+    const int fy1 = min(fy + 1, frows - 1);               // replicate at the true bottom border only
+    const uint8_t* p0 = P + (size_t)fy * fpitch;
+    const uint8_t* p1 = P + (size_t)fy1 * fpitch;
+    const uint8_t* n0 = N + (size_t)fy * fpitch;
+    const uint8_t* n1 = N + (size_t)fy1 * fpitch;
+    uint32_t opk[4];
+    float oit[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int x = x0 + i;
+        int gx = 0, gy = 0, gt = 0;
+        if (x < g.W) {
+            const int x1 = min(x + 1, g.W - 1);
+            const int a00 = p0[x], a01 = p0[x1], a10 = p1[x], a11 = p1[x1];
+            const int c00 = n0[x], c01 = n0[x1], c10 = n1[x], c11 = n1[x1];
+            gx = (a01 - a00) + (a11 - a10) + (c01 - c00) + (c11 - c10);      // 4 * Ix
+            gy = (a10 - a00) + (a11 - a01) + (c10 - c00) + (c11 - c01);      // 4 * Iy
+            gt = (c00 + c01 + c10 + c11) - (a00 + a01 + a10 + a11);          // 4 * It
+        }
+        opk[i] = pack_coef(gx, gy, 0);
+        oit[i] = __fmul_rn((float)gt, 0.25f);
+    }
+    const size_t o = (size_t)b * g.plane + (size_t)y * g.pitch + x0;
+    *reinterpret_cast<uint4*>(cpk + o) = make_uint4(opk[0], opk[1], opk[2], opk[3]);
+    *reinterpret_cast<float4*>(itp + o) = make_float4(oit[0], oit[1], oit[2], oit[3]);
+}
+
+// K2 for the textbook mode: one weighted-average sweep, one pixel per thread
+__global__ void __launch_bounds__(256)
+k_jacobi_generic_tb(const float* __restrict__ u, const float* __restrict__ v,
+                    float* __restrict__ un, float* __restrict__ vn,
+                    const uint32_t* __restrict__ cpk, const float* __restrict__ itp, Geom g, float alpha2) {
+    const int x = blockIdx.x * 32 + threadIdx.x;
+    const int y = g.oy0 + blockIdx.y * 8 + threadIdx.y;
+    if (x >= g.W || y >= g.oy1) return;
+    const size_t base = (size_t)blockIdx.z * g.plane;
+    auto bar = [&](const float* P) {
+        auto tap = [&](int yy, int xx) {
+            return (yy >= 0 && yy < g.H && xx >= 0 && xx < g.W) ? P[(size_t)yy * g.pitch + xx] : 0.f;
+        };
+        auto h = [&](int yy) { return __fmaf_rn(2.f, tap(yy, x), __fadd_rn(tap(yy, x - 1), tap(yy, x + 1))); };
+        const float V = __fmaf_rn(2.f, h(y), __fadd_rn(h(y - 1), h(y + 1)));
+        return tb_bar(V, tap(y, x));
+    };
+    const size_t o = base + (size_t)y * g.pitch + x;
+    float ix, iy, nu, nv;
+    unpack_coef_tb(cpk[o], ix, iy);
+    hs_update_bar(bar(u + base), bar(v + base), ix, iy, itp[o], hs_inv(ix, iy, alpha2), nu, nv);
+    un[o] = nu;
+    vn[o] = nv;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -410,7 +500,17 @@ __device__ __forceinline__ void row_sums(const float (&a)[4], float (&h)[4]) {
     paired_sums<RL, RR>(s, p, h);
 }
 
-template <int RL, int RR, int R, int NWARP, bool MASKED>
+// row sums of the textbook mode: h = x[-1] + 2 x[0] + x[1]
+__device__ __forceinline__ void row_sums_tb(const float (&a)[4], float (&h)[4]) {
+    const float l = __shfl_up_sync(0xffffffffu, a[3], 1);
+    const float r = __shfl_down_sync(0xffffffffu, a[0], 1);
+    h[0] = __fmaf_rn(2.f, a[0], __fadd_rn(l, a[1]));
+    h[1] = __fmaf_rn(2.f, a[1], __fadd_rn(a[0], a[2]));
+    h[2] = __fmaf_rn(2.f, a[2], __fadd_rn(a[1], a[3]));
+    h[3] = __fmaf_rn(2.f, a[3], __fadd_rn(a[2], r));
+}
+
+template <int RL, int RR, int R, int NWARP, bool MASKED, bool TB>
 __device__ __forceinline__ void tile_sweeps(float (&u)[R][4], float (&v)[R][4],
                                             const float (&ix)[R][4], const float (&iy)[R][4],
                                             const float (&it)[R][4], const float (&iv)[R][4],
@@ -427,8 +527,8 @@ __device__ __forceinline__ void tile_sweeps(float (&u)[R][4], float (&v)[R][4],
         float hu[R][4], hv[R][4];
 #pragma unroll
         for (int j = 0; j < R; ++j) {
-            row_sums<RL, RR>(u[j], hu[j]);
-            row_sums<RL, RR>(v[j], hv[j]);
+            if (TB) { row_sums_tb(u[j], hu[j]); row_sums_tb(v[j], hv[j]); }
+            else { row_sums<RL, RR>(u[j], hu[j]); row_sums<RL, RR>(v[j], hv[j]); }
             if (TS::slot(j) >= 0) {  // rows a vertical neighbour will need
                 const size_t o = ((size_t)warp * TS::NSLOT + TS::slot(j)) * TS::SX + lane * 4;
                 *reinterpret_cast<float4*>(exu + o) = make_float4(hu[j][0], hu[j][1], hu[j][2], hu[j][3]);
@@ -450,6 +550,22 @@ __device__ __forceinline__ void tile_sweeps(float (&u)[R][4], float (&v)[R][4],
         };
         auto update_row = [&](int j, const float (&au)[RL > 0 ? RL : 1][4], const float (&av)[RL > 0 ? RL : 1][4],
                               const float (&bu)[RR > 0 ? RR : 1][4], const float (&bv)[RR > 0 ? RR : 1][4]) {
+            if constexpr (TB) {   // weighted average: V = h[j-1] + 2 h[j] + h[j+1], ubar = V/12 - u/3
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    const float Vu = __fmaf_rn(2.f, hu[j][c], __fadd_rn(column_term(hu, au, bu, j - 1, c), column_term(hu, au, bu, j + 1, c)));
+                    const float Vv = __fmaf_rn(2.f, hv[j][c], __fadd_rn(column_term(hv, av, bv, j - 1, c), column_term(hv, av, bv, j + 1, c)));
+                    float nu, nv;
+                    hs_update_bar(tb_bar(Vu, u[j][c]), tb_bar(Vv, v[j][c]), ix[j][c], iy[j][c], it[j][c], iv[j][c], nu, nv);
+                    if (MASKED) {
+                        const bool in = (inmask >> (j * 4 + c)) & 1u;
+                        nu = in ? nu : 0.f;
+                        nv = in ? nv : 0.f;
+                    }
+                    u[j][c] = nu;
+                    v[j][c] = nv;
+                }
+            } else {
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
                 float su = 0.f, sv = 0.f;
@@ -491,6 +607,7 @@ __device__ __forceinline__ void tile_sweeps(float (&u)[R][4], float (&v)[R][4],
                 }
                 u[j][c] = nu;
                 v[j][c] = nv;
+            }
             }
         };
         float au[RL > 0 ? RL : 1][4], av[RL > 0 ? RL : 1][4];
@@ -572,14 +689,15 @@ __device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.pr
 // TMA boxes of the next item into the free stage (empty[] -> full[] mbarriers) and publishes this
 // CTA's finished tiles (stored[] mbarrier -> fence -> counter), polling all of that without ever
 // blocking on one duty, so a CTA can never hold back a tile somebody else is waiting for.
-template <int RL, int RR, int R, int NWARP>
+template <int RL, int RR, int R, int NWARP, bool TB = false>
 __global__ void __launch_bounds__(NWARP * 32 + 128, 1)
 k_jacobi_tile(const __grid_constant__ CUtensorMap tm_u0, const __grid_constant__ CUtensorMap tm_v0,
               const __grid_constant__ CUtensorMap tm_u1, const __grid_constant__ CUtensorMap tm_v1,
               const __grid_constant__ CUtensorMap tm_cpk, const __grid_constant__ CUtensorMap tm_inv,
               float* __restrict__ u0, float* __restrict__ v0, float* __restrict__ u1, float* __restrict__ v1,
-              int* __restrict__ done, Geom g, TileGrid tg, float kf) {
+              int* __restrict__ done, Geom g, TileGrid tg, float kf, float alpha2) {
     using TS = TileShape<RL, RR, R, NWARP>;
+    static_assert(!TB || (RL == 1 && RR == 1), "the textbook average is a 3x3 stencil");
     static_assert(R * 4 <= 32, "in-image mask is one 32-bit word per thread");
     static_assert(RL <= 4 && RR <= 4, "horizontal neighbours come from the adjacent lane only");
     static_assert(NWARP % 4 == 0, "setmaxnreg acts on whole warp groups");
@@ -787,11 +905,21 @@ k_jacobi_tile(const __grid_constant__ CUtensorMap tm_u0, const __grid_constant__
             const uint4 qc = *reinterpret_cast<const uint4*>(s_cpk + so);
             u[j][0] = qu.x; u[j][1] = qu.y; u[j][2] = qu.z; u[j][3] = qu.w;
             v[j][0] = qv.x; v[j][1] = qv.y; v[j][2] = qv.z; v[j][3] = qv.w;
-            iv[j][0] = qi.x; iv[j][1] = qi.y; iv[j][2] = qi.z; iv[j][3] = qi.w;
-            unpack_coef(qc.x, ix[j][0], iy[j][0], it[j][0]);
-            unpack_coef(qc.y, ix[j][1], iy[j][1], it[j][1]);
-            unpack_coef(qc.z, ix[j][2], iy[j][2], it[j][2]);
-            unpack_coef(qc.w, ix[j][3], iy[j][3], it[j][3]);
+            if (TB) {       // second plane = It; inv from the gradients
+                it[j][0] = qi.x; it[j][1] = qi.y; it[j][2] = qi.z; it[j][3] = qi.w;
+                unpack_coef_tb(qc.x, ix[j][0], iy[j][0]);
+                unpack_coef_tb(qc.y, ix[j][1], iy[j][1]);
+                unpack_coef_tb(qc.z, ix[j][2], iy[j][2]);
+                unpack_coef_tb(qc.w, ix[j][3], iy[j][3]);
+#pragma unroll
+                for (int c = 0; c < 4; ++c) iv[j][c] = hs_inv(ix[j][c], iy[j][c], alpha2);
+            } else {
+                iv[j][0] = qi.x; iv[j][1] = qi.y; iv[j][2] = qi.z; iv[j][3] = qi.w;
+                unpack_coef(qc.x, ix[j][0], iy[j][0], it[j][0]);
+                unpack_coef(qc.y, ix[j][1], iy[j][1], it[j][1]);
+                unpack_coef(qc.z, ix[j][2], iy[j][2], it[j][2]);
+                unpack_coef(qc.w, ix[j][3], iy[j][3], it[j][3]);
+            }
         }
         // Everyone has (a) finished the previous tile - its exchange scratch in the OTHER stage is
         // dead - and (b) pulled this tile out of THIS stage, which now becomes the exchange scratch.
@@ -806,9 +934,9 @@ k_jacobi_tile(const __grid_constant__ CUtensorMap tm_u0, const __grid_constant__
         float* s_ex = reinterpret_cast<float*>(st);
         const int kk = min(tg.k, tg.sweeps - cur.p * tg.k);
         if (tile_inside)
-            tile_sweeps<RL, RR, R, NWARP, false>(u, v, ix, iy, it, iv, s_ex, kk, kf, warp, lane, inmask);
+            tile_sweeps<RL, RR, R, NWARP, false, TB>(u, v, ix, iy, it, iv, s_ex, kk, kf, warp, lane, inmask);
         else
-            tile_sweeps<RL, RR, R, NWARP, true>(u, v, ix, iy, it, iv, s_ex, kk, kf, warp, lane, inmask);
+            tile_sweeps<RL, RR, R, NWARP, true, TB>(u, v, ix, iy, it, iv, s_ex, kk, kf, warp, lane, inmask);
 
         HS_PROF_T(pt3);
         // store the exact centre of the tile into the other pair of planes
@@ -849,6 +977,21 @@ k_widen(const float* __restrict__ a, const float* __restrict__ b2, double* __res
     for (long long p = i; p < n; p += stride) {
         oa[p] = (double)a[p];
         ob[p] = (double)b2[p];
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+k_unpack_grad_tb(const uint32_t* __restrict__ cpk, const float* __restrict__ itp, T* __restrict__ gx,
+                 T* __restrict__ gy, T* __restrict__ gt, long long n) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long p = i; p < n; p += stride) {
+        float ix, iy;
+        unpack_coef_tb(cpk[p], ix, iy);
+        gx[p] = (T)ix;
+        gy[p] = (T)iy;
+        gt[p] = (T)itp[p];
     }
 }
 

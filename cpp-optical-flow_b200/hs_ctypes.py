@@ -9,7 +9,7 @@ from . import _build
 
 HS_OK = 0
 HS_F32, HS_F64 = 0, 1
-FLAG_TOP_IS_SEAM, FLAG_BOTTOM_IS_SEAM, FLAG_FORCE_GENERIC, FLAG_SINGLE_PHASE = 1, 2, 4, 8
+FLAG_TOP_IS_SEAM, FLAG_BOTTOM_IS_SEAM, FLAG_FORCE_GENERIC, FLAG_SINGLE_PHASE, FLAG_TEXTBOOK = 1, 2, 4, 8, 16
 
 STATUS_NAMES = {0: "HS_OK", 1: "HS_ERR_INVALID_ARG", 2: "HS_ERR_CUDA", 3: "HS_ERR_OOM",
                 4: "HS_ERR_UNSUPPORTED", 5: "HS_ERR_STATE"}

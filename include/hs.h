@@ -58,6 +58,11 @@ typedef enum hs_dtype { HS_F32 = 0, HS_F64 = 1 } hs_dtype;
 #define HS_FLAG_BOTTOM_IS_SEAM 0x2 /* row-slab: rows exist below this context's buffer          */
 #define HS_FLAG_FORCE_GENERIC 0x4  /* always use the one-sweep-per-launch kernel (A/B testing)  */
 #define HS_FLAG_SINGLE_PHASE 0x8   /* one launch per k fused sweeps (no multi-phase dataflow launch) */
+#define HS_FLAG_TEXTBOOK 0x10      /* NOT the reference's arithmetic: Horn & Schunck's 2x2x2-cube gradients
+                                      and 1/6-1/12 weighted 3x3 average (what BASELINE.json's prose
+                                      describes); window_size must be 3; checked against its own NumPy
+                                      oracle (oracle/hs_oracle.py::np_flow_textbook), never against the
+                                      reference                                                       */
 
 /*
  * Replaces the three public fields + constructor of class hornSchunck (hornSchunck.cpp:10-17)

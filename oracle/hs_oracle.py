@@ -149,6 +149,46 @@ def np_flow(prev_u8, next_u8, w: int, iters: int, alpha: float, dtype=np.float64
 
 
 # --------------------------------------------------------------------------------------
+# oracle of the NON-PARITY "textbook" mode (HS_FLAG_TEXTBOOK).  The reference does not compute this;
+# it is the discretisation BASELINE.json's prose describes (Horn & Schunck 1981): gradients over
+# the 2x2x2 cube (replicated at the right/bottom border), 1/6 - 1/12 weighted 3x3 average with
+# zero padding.  The commented-out two-frame average at hornSchunck.cpp:30-36 hints at it.
+# --------------------------------------------------------------------------------------
+def np_gradients_textbook(prev_u8, next_u8, dtype=np.float64):
+    P = np.pad(prev_u8.astype(dtype), ((0, 1), (0, 1)), mode="edge")
+    N = np.pad(next_u8.astype(dtype), ((0, 1), (0, 1)), mode="edge")
+    a00, a01, a10, a11 = P[:-1, :-1], P[:-1, 1:], P[1:, :-1], P[1:, 1:]
+    c00, c01, c10, c11 = N[:-1, :-1], N[:-1, 1:], N[1:, :-1], N[1:, 1:]
+    q = dtype(0.25)
+    gx = q * ((a01 - a00) + (a11 - a10) + (c01 - c00) + (c11 - c10))
+    gy = q * ((a10 - a00) + (a11 - a01) + (c10 - c00) + (c11 - c01))
+    gt = q * ((c00 + c01 + c10 + c11) - (a00 + a01 + a10 + a11))
+    return gx, gy, gt
+
+
+def np_flow_textbook(prev_u8, next_u8, iters: int, alpha: float, dtype=np.float64):
+    dt = np.dtype(dtype).type
+    gx, gy, gt = np_gradients_textbook(prev_u8, next_u8, dtype)
+    u = np.zeros_like(gt)
+    v = np.zeros_like(gt)
+    den = dt(alpha) ** 2 + gx * gx + gy * gy
+
+    def bar(f):
+        p = np.pad(f, 1)
+        nsew = p[:-2, 1:-1] + p[2:, 1:-1] + p[1:-1, :-2] + p[1:-1, 2:]
+        diag = p[:-2, :-2] + p[:-2, 2:] + p[2:, :-2] + p[2:, 2:]
+        return nsew / dt(6) + diag / dt(12)
+
+    with np.errstate(divide="ignore", invalid="ignore"):
+        for _ in range(iters):
+            ua, va = bar(u), bar(v)
+            c = (gx * ua + gy * va + gt) / den
+            u = ua - gx * c
+            v = va - gy * c
+    return gx, gy, gt, u, v
+
+
+# --------------------------------------------------------------------------------------
 # restatement of plotFlow.cpp - only needed to compare with the reference's golden PNGs
 # --------------------------------------------------------------------------------------
 def _ctrunc(x: float) -> int:

@@ -197,6 +197,33 @@ def test_grid_sampler_feeds_the_reference_plot(pkg, oracle, kitti):
     assert int((img[yx[:, 0], yx[:, 1]] != gold["bgr"]).any(axis=1).sum()) <= 20
 
 
+@pytest.mark.parametrize("shape,iters,k", [((64, 96), 1, 0), ((97, 150), 40, 0), ((200, 333), 25, 4), ((375, 1242), 60, 6)])
+def test_textbook_mode_matches_its_own_oracle(pkg, oracle, shape, iters, k):
+    """SURVEY 8f row 4 (NOT a parity item): cube gradients + 1/6-1/12 weighted average, the scheme
+    BASELINE.json's prose describes.  Checked against oracle.np_flow_textbook and fused == generic."""
+    from cpp_optical_flow_b200 import hs_ctypes as H, synth
+    a, b = synth.frame_pair(shape[0], shape[1], seed=shape[0], shape=None) if False else synth.frame_pair(shape[0], shape[1], seed=shape[0])
+    ogx, ogy, ogt, ou, ov = oracle.np_flow_textbook(a, b, iters, 1.0)
+    with pkg.Solver(shape[1], shape[0], 3, iters, 1.0, temporal_k=k, flags=H.FLAG_TEXTBOOK) as s:
+        gx, gy, gt = s.gradients(a, b)
+        u, v = s.solve(a, b, np.float64)
+        assert s.timing().kernel_id == 1
+    assert np.array_equal(gx, ogx) and np.array_equal(gy, ogy) and np.array_equal(gt, ogt)   # multiples of 1/4: exact
+    assert_flow_close(u, v, ou, ov)
+    with pkg.Solver(shape[1], shape[0], 3, iters, 1.0, flags=H.FLAG_TEXTBOOK | H.FLAG_FORCE_GENERIC) as s:
+        gu, gv = s.solve(a, b, np.float64)
+    assert np.array_equal(u, gu) and np.array_equal(v, gv)
+    # a pure translation by (1.0, 0.5) px: the textbook gradients are in pixel units (no factor 8)
+    if iters >= 40:
+        assert abs(np.median(u) - 1.0) < 0.35 and abs(np.median(v) - 0.5) < 0.35
+
+
+def test_textbook_mode_needs_window_3(pkg):
+    from cpp_optical_flow_b200 import hs_ctypes as H
+    with pytest.raises(H.HsError):
+        pkg.Solver(32, 32, 5, 3, 1.0, flags=H.FLAG_TEXTBOOK)
+
+
 # ---------------------------------------------------------------- invariances (bit-exact)
 @pytest.mark.parametrize("w,k", [(3, 1), (3, 2), (3, 3), (3, 4), (3, 7), (3, 12), (5, 1), (5, 2), (5, 3), (5, 5),
                                  (2, 4), (2, 9), (4, 2), (4, 3)])
