@@ -394,18 +394,21 @@ __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
 }
 
 // ------------------------------------------------------------------------------------------
-// K3: k fused Jacobi sweeps per launch (temporal blocking), persistent CTAs.
+// K3: ALL sweeps of a solve in one launch: phases of k fused sweeps (temporal blocking) over
+// staged tiles, persistent warp-specialised CTAs, dataflow synchronisation between tiles.
 //
-// One CTA per SM walks over staged tiles of SX x SY pixels (SX = 128 = 32 lanes x 4 px,
-// SY = NWARP x R rows), tile = blockIdx.x, blockIdx.x + gridDim.x, ...  Per tile:
+// One CTA per SM (12 compute warps + a producer warp group) walks over staged tiles of SX x SY
+// pixels (SX = 128 = 32 lanes x 4 px, SY = NWARP x R rows).  Per tile:
 //   * four TMA boxes (u, v, packed Ix/Iy/It, inv) land in one of TWO shared-memory stages; the
-//     boxes of the NEXT tile are issued as soon as this tile's registers are loaded, so they
-//     stream in underneath the k sweeps of this tile (mbarrier full[stage], parity = use count)
+//     producer issues the boxes of the NEXT tile as soon as the compute warps have pulled this
+//     tile into registers, so they stream in underneath the k sweeps of this tile
+//     (mbarriers full[stage] / empty[stage])
 //   * each thread keeps its 4 x R patch of u, v AND its coefficients in registers for all k sweeps
 //   * per sweep: (1) row sums of the patch, horizontal neighbours by warp shuffle; (2) the rows a
 //     vertical neighbour needs go to a double-buffered exchange array (it lives in the stage the
-//     tile came from, which is dead once the registers are loaded); (3) one __syncthreads;
-//     (4) neighbour rows come back, box sum, update in place
+//     tile came from, which is dead once the registers are loaded); (3) the rows whose window
+//     stays inside the patch are updated; (4) one named barrier of the compute warps; (5) the
+//     neighbour rows come back, the remaining rows are updated in place
 // The ring of pixels whose dependency cone leaves the staged tile grows by (a, w/2) per sweep,
 // so after k sweeps the centre VX x VY pixels are exact and are the only ones stored.
 // Pixels outside the image must be 0 at EVERY sweep (BORDER_CONSTANT): TMA zero-fill gives that

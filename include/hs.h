@@ -78,7 +78,7 @@ typedef struct hs_config {
     double alpha;           /* alpha (:11,16); 0 is legal and yields IEEE nan/inf like upstream   */
     int32_t batch;          /* independent frame pairs solved per call (default 1)                */
     int32_t device;         /* CUDA ordinal; -1 = current device                                  */
-    int32_t temporal_k;     /* sweeps fused per launch (temporal blocking); 0 = auto              */
+    int32_t temporal_k;     /* sweeps fused per phase (temporal blocking depth k); 0 = auto       */
     uint32_t flags;         /* HS_FLAG_*                                                          */
     /* Row-slab decomposition (one context per GPU).  The context's buffer holds `height` rows of
      * a taller image; it produces rows [out_row_begin, out_row_end) and treats the other rows as
@@ -99,7 +99,7 @@ typedef struct hs_timing {
     float d2h_ms;     /* widen + device->host                            */
     float total_ms;
     int32_t launches;   /* kernels launched by the last call              */
-    int32_t temporal_k; /* fused sweeps per launch actually used          */
+    int32_t temporal_k; /* sweeps fused per phase (temporal blocking depth)*/
     int32_t kernel_id;  /* 0 = generic one-sweep kernel, 1 = fused tile kernel */
 } hs_timing;
 
@@ -157,7 +157,10 @@ int hs_upload(hs_ctx* ctx,                                    /* host uint8 -> d
               const uint8_t* prev, size_t prev_row_stride, size_t prev_image_stride,
               const uint8_t* next, size_t next_row_stride, size_t next_image_stride);
 int hs_prepare(hs_ctx* ctx);                                  /* gradients+coefficients, u=v=0   */
-int hs_iterate(hs_ctx* ctx, int iterations);                  /* `iterations` more Jacobi sweeps */
+/* `iterations` more Jacobi sweeps.  Whole-image contexts run them as ONE launch of ceil(n/k) phases
+ * (tiles synchronise through per-tile counters); row-slab contexts and small images launch once
+ * per k sweeps, so that the host can refresh halos in between. */
+int hs_iterate(hs_ctx* ctx, int iterations);
 /* Row-slab helper: `sweeps` (<= temporal_k) fused sweeps producing only buffer rows
  * [row_begin, row_end) of the NEXT flow planes (any rows of the buffer, halo rows included); the
  * current planes become the next ones when `flip` is non-zero (pass it on the last partial launch
