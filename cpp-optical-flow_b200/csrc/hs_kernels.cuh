@@ -830,10 +830,12 @@ k_jacobi_tile(const __grid_constant__ CUtensorMap tm_u0, const __grid_constant__
                         else if (now - t0 > WAIT_LIMIT_NS) __trap();
                     }
                 }
-                if (lane == 0) {
-                    fence_acq_rel_gpu();              // acquire: the neighbours' stores are visible ...
-                    fence_proxy_async_all();          // ... also to the async proxy (TMA) reads issued below
-                }
+                // Acquire on EVERY lane that observed a counter (relaxed load + fence is the acquire
+                // pattern of the thread that loaded), then a warp barrier carries the ordering over
+                // to lane 0, whose proxy fence extends it to the async-proxy (TMA) reads issued below.
+                fence_acq_rel_gpu();
+                __syncwarp();
+                if (lane == 0) fence_proxy_async_all();
             }
 #ifdef HS_TILE_PROFILE
             const long long prof_t1 = clock64();
