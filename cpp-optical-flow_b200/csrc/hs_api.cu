@@ -67,6 +67,7 @@ struct hs_ctx {
     void* d_out = nullptr;
     size_t out_bytes = 0;
     uint8_t* d_bgr = nullptr;    // staging for hs_solve_bgr: two 8UC3 frames
+    unsigned int* d_resid = nullptr;   // hs_iterate_until: max-abs-difference accumulator
     // streaming front-end (hs_video_*): frame ring, copy stream, double-buffered output staging
     uint8_t* d_ring[3] = {nullptr, nullptr, nullptr};   // [0], [1] are the context's own prev/next
     void* d_vout[2] = {nullptr, nullptr};
@@ -378,7 +379,7 @@ void destroy_impl(hs_ctx* c) {
         for (auto& e : c->ev_k1) if (e) cudaEventDestroy(e);
         for (auto& e : c->ev_solved) if (e) cudaEventDestroy(e);
         for (int i = 0; i < 2; ++i) { cudaFree(c->d_u[i]); cudaFree(c->d_v[i]); }
-        cudaFree(c->d_cpk); cudaFree(c->d_inv); cudaFree(c->d_done); cudaFree(c->d_bgr); cudaFree(c->d_out);
+        cudaFree(c->d_cpk); cudaFree(c->d_inv); cudaFree(c->d_done); cudaFree(c->d_bgr); cudaFree(c->d_resid); cudaFree(c->d_out);
         for (auto& e : c->ev) if (e) cudaEventDestroy(e);
         if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
     }
@@ -578,6 +579,37 @@ int hs_iterate_rows(hs_ctx* c, int sweeps, int row_begin, int row_end, int flip)
     if (e != cudaSuccess) return fail(c, HS_ERR_CUDA, "sweep launch failed: %s", cudaGetErrorString(e));
     c->timing.launches += 1;
     if (flip) c->cur ^= 1;
+    return HS_OK;
+}
+
+int hs_iterate_until(hs_ctx* c, int max_sweeps, double tolerance, int check_every, int* sweeps_done, double* residual) {
+    if (!c) return HS_ERR_INVALID_ARG;
+    if (!c->prepared) return fail(c, HS_ERR_STATE, "hs_iterate_until before hs_prepare");
+    if (max_sweeps < 0 || check_every < 1 || !(tolerance >= 0)) return fail(c, HS_ERR_INVALID_ARG, "bad early-exit arguments");
+    if (c->top_seam || c->bot_seam) return fail(c, HS_ERR_UNSUPPORTED, "hs_iterate_until needs a whole-image context");
+    DevGuard g(c->dev);
+    if (!c->d_resid) HS_CUDA(c, cudaMalloc(&c->d_resid, sizeof(unsigned int)));
+    int done = 0, rc;
+    float r = __builtin_inff();
+    while (done < max_sweeps) {
+        const int chunk = std::min(check_every, max_sweeps - done);
+        // the last sweep of a chunk runs alone, so that the two plane pairs hold consecutive iterates
+        if (chunk > 1 && (rc = do_iterate(c, chunk - 1))) return rc;
+        if ((rc = do_iterate(c, 1))) return rc;
+        done += chunk;
+        HS_CUDA(c, cudaMemsetAsync(c->d_resid, 0, sizeof(unsigned int), c->stream));
+        hs::k_max_abs_diff<<<148 * 4, 256, 0, c->stream>>>(c->d_u[c->cur ^ 1], c->d_u[c->cur], c->d_v[c->cur ^ 1],
+                                                          c->d_v[c->cur], c->geom(), c->B, c->d_resid);
+        HS_CUDA(c, cudaGetLastError());
+        c->timing.launches += 1;
+        unsigned int bits = 0;
+        HS_CUDA(c, cudaMemcpyAsync(&bits, c->d_resid, sizeof bits, cudaMemcpyDeviceToHost, c->stream));
+        HS_CUDA(c, cudaStreamSynchronize(c->stream));
+        memcpy(&r, &bits, sizeof r);
+        if (r <= (float)tolerance) break;
+    }
+    if (sweeps_done) *sweeps_done = done;
+    if (residual) *residual = (double)r;
     return HS_OK;
 }
 

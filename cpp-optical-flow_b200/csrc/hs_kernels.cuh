@@ -1000,6 +1000,30 @@ k_unpack_grad_tb(const uint32_t* __restrict__ cpk, const float* __restrict__ itp
     }
 }
 
+// max(|a1-a0|, |b1-b0|) over a pitched plane pair (rows [row0,row1), W columns, `batch` images):
+// the residual of the early-exit extension.  Non-negative floats order like their bit patterns,
+// so the grid-wide maximum is an atomicMax on the raw bits; NaN counts as +inf.
+__global__ void __launch_bounds__(256)
+k_max_abs_diff(const float* __restrict__ a0, const float* __restrict__ a1, const float* __restrict__ b0,
+               const float* __restrict__ b1, Geom g, int batch, unsigned int* __restrict__ out) {
+    const int rows = g.oy1 - g.oy0;
+    const long long per = (long long)rows * g.W;
+    const long long n = per * batch;
+    float m = 0.f;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const int b = (int)(i / per);
+        const long long r = i - (long long)b * per;
+        const int y = g.oy0 + (int)(r / g.W), x = (int)(r % g.W);
+        const size_t o = (size_t)b * g.plane + (size_t)y * g.pitch + x;
+        float d = fmaxf(fabsf(a1[o] - a0[o]), fabsf(b1[o] - b0[o]));
+        if (!(d == d) || !(a1[o] == a1[o]) || !(b1[o] == b1[o])) d = __int_as_float(0x7f800000);
+        m = fmaxf(m, d);
+    }
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, s));
+    if ((threadIdx.x & 31) == 0) atomicMax(out, __float_as_uint(m));
+}
+
 // Flow samples on the plot grid: plotFlow::plotBresenhamLine reads u, v only at rows/columns that
 // are multiples of `delta` (plotFlow.cpp:70-75); this gathers just those (row-major grid order).
 __global__ void __launch_bounds__(256)

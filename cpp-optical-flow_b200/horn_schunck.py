@@ -172,6 +172,13 @@ class Solver:
     def iterate_rows(self, sweeps, row_begin, row_end, flip):
         self._check(self._lib.hs_iterate_rows(self._ctx, int(sweeps), int(row_begin), int(row_end), int(bool(flip))))
 
+    def iterate_until(self, max_sweeps, tolerance, check_every=50):
+        """Early exit (extension): -> (sweeps done, residual of the last sweep)."""
+        done, res = C.c_int(0), C.c_double(0.0)
+        self._check(self._lib.hs_iterate_until(self._ctx, int(max_sweeps), float(tolerance), int(check_every),
+                                               C.byref(done), C.byref(res)))
+        return done.value, res.value
+
     def solve_device(self):
         self._check(self._lib.hs_solve_device(self._ctx))
 

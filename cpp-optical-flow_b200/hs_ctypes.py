@@ -16,7 +16,7 @@ STATUS_NAMES = {0: "HS_OK", 1: "HS_ERR_INVALID_ARG", 2: "HS_ERR_CUDA", 3: "HS_ER
 
 # every extern "C" symbol include/hs.h declares (tests check the library exports all of them)
 SYMBOLS = ["hs_create", "hs_destroy", "hs_solve", "hs_solve_bgr", "hs_gradients", "hs_upload", "hs_prepare",
-           "hs_iterate", "hs_iterate_rows", "hs_solve_device", "hs_download", "hs_sync", "hs_sample_grid", "hs_get_device_view",
+           "hs_iterate", "hs_iterate_rows", "hs_iterate_until", "hs_solve_device", "hs_download", "hs_sync", "hs_sample_grid", "hs_get_device_view",
            "hs_video_push", "hs_video_flush", "hs_video_reset", "hs_get_timing", "hs_last_error", "hs_version", "hs_host_alloc", "hs_host_free"]
 
 
@@ -76,6 +76,7 @@ def load_library(path: str | None = None):
     lib.hs_prepare.argtypes = [vp]
     lib.hs_iterate.argtypes = [vp, i32]
     lib.hs_iterate_rows.argtypes = [vp, i32, i32, i32, i32]
+    lib.hs_iterate_until.argtypes = [vp, i32, C.c_double, i32, C.POINTER(C.c_int), C.POINTER(C.c_double)]
     lib.hs_solve_device.argtypes = [vp]
     lib.hs_download.argtypes = [vp, vp, sz, sz, vp, sz, sz, i32]
     lib.hs_sync.argtypes = [vp]

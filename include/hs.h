@@ -168,6 +168,12 @@ int hs_iterate(hs_ctx* ctx, int iterations);
  * and overlap it with the interior rows, and (b) keep a halo several launches deep and advance
  * part of it redundantly, so that halos are exchanged only every few launches. */
 int hs_iterate_rows(hs_ctx* ctx, int sweeps, int row_begin, int row_end, int flip);
+/* Early exit (contract extension, the reference always runs maxIterations sweeps, hornSchunck.cpp:56):
+ * sweeps in chunks of `check_every`; after each chunk the residual max(|u_n - u_{n-1}|, |v_n - v_{n-1}|)
+ * of the last sweep is reduced on the device; stops at the first chunk whose residual is <= tolerance,
+ * or after max_sweeps.  The flow after *sweeps_done sweeps is bit-identical to hs_iterate(*sweeps_done). */
+int hs_iterate_until(hs_ctx* ctx, int max_sweeps, double tolerance, int check_every, int* sweeps_done,
+                     double* residual);
 int hs_solve_device(hs_ctx* ctx);                             /* prepare + iterate(max_iterations)*/
 int hs_download(hs_ctx* ctx,                                  /* device u,v -> host              */
                 void* u, size_t u_row_stride, size_t u_image_stride,

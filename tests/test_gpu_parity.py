@@ -218,6 +218,30 @@ def test_textbook_mode_matches_its_own_oracle(pkg, oracle, shape, iters, k):
         assert abs(np.median(u) - 1.0) < 0.35 and abs(np.median(v) - 0.5) < 0.35
 
 
+def test_early_exit_stops_on_the_residual(pkg, oracle):
+    """Contract extension: residual-based early exit.  The residual equals the oracle's, the stop
+    happens at the first check that meets the tolerance, and the state is that of a fixed-T solve."""
+    from cpp_optical_flow_b200 import synth
+    a, b = synth.frame_pair(120, 200, seed=4)
+    with pkg.Solver(200, 120, 3, 400, 1.0) as s:
+        s.upload(a, b); s.prepare()
+        done, res = s.iterate_until(400, 2e-4, check_every=20)
+        u, v = s.download(np.float32)
+        assert 20 <= done < 400 and done % 20 == 0 and res <= 2e-4
+        s.prepare(); s.iterate(done); u2, v2 = s.download(np.float32)
+        assert np.array_equal(u, u2) and np.array_equal(v, v2)
+        s.prepare()
+        d2, r2 = s.iterate_until(60, 0.0, check_every=25)       # tolerance never met: runs to the cap
+        assert d2 == 60 and r2 > 0
+    # the oracle's residual history: first multiple of 20 with residual <= tol is where we stopped
+    *_, pu, pv = oracle.np_flow(a, b, 3, done - 1, 1.0)
+    *_, cu, cv_ = oracle.np_flow(a, b, 3, done, 1.0)
+    assert abs(max(np.abs(cu - pu).max(), np.abs(cv_ - pv).max()) - res) < 2e-5
+    *_, pu, pv = oracle.np_flow(a, b, 3, done - 21, 1.0)
+    *_, cu, cv_ = oracle.np_flow(a, b, 3, done - 20, 1.0)
+    assert max(np.abs(cu - pu).max(), np.abs(cv_ - pv).max()) > 2e-4 - 2e-5
+
+
 def test_textbook_mode_needs_window_3(pkg):
     from cpp_optical_flow_b200 import hs_ctypes as H
     with pytest.raises(H.HsError):
