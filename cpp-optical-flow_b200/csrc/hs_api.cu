@@ -499,7 +499,13 @@ int hs_create(const hs_config* cfg_in, hs_ctx** out) {
     if (have_tile) {
         using TS0 = hs::TileShape<1, 1, TILE_R, TILE_NWARP>;
         int k = cfg.temporal_k > 0 ? cfg.temporal_k : env_int("HS_K", 0);
-        if (k <= 0) k = std::max(1, 6 / std::max(1, std::max(c->RL, c->RR)));   // measured on B200: w=3 -> 6, w=5 -> 3
+        if (k <= 0) {
+            // measured on B200 (profiles/*k_sweep*): radius-1 windows want k=6 when the planes stream
+            // from HBM (fewer bytes per sweep) but k=4 when the 24 B/pixel working set sits in L2
+            // (better valid fraction per staged tile); radius-2 windows k=3
+            const bool l2_resident = (double)c->plane * c->B * 24.0 <= 64.0e6;
+            k = std::max(c->RL, c->RR) <= 1 ? (l2_resident ? 4 : 6) : 3;
+        }
         k = std::min(k, kmax);
         // keep a useful centre: at least a quarter of the staged rows must be output rows
         while (k > 1 && TS0::SY - (c->RL + c->RR) * k < TS0::SY / 4) --k;

@@ -434,7 +434,8 @@ struct TileShape {
     static constexpr size_t BYTES_EX = 2 * 2 * EX_FIELD * 4;
     static_assert(BYTES_EX <= STAGE, "exchange array must fit in one stage");
     static constexpr size_t OFF_BAR = 2 * STAGE;
-    static constexpr size_t SMEM = OFF_BAR + 64;                      // full[2], empty[2], stored[2]
+    static constexpr size_t OFF_INFO = OFF_BAR + 64;                  // int4 x 2: decoded (x0, y0, pair, phase) of the staged items
+    static constexpr size_t SMEM = OFF_INFO + 32;                     // full[2], empty[2], stored[2]; item info
     static constexpr uint32_t TX_BYTES = (uint32_t)STAGE;
     // slot of patch row j in the exchange array (-1: no neighbour reads it)
     __host__ __device__ static constexpr int slot(int j) {
@@ -759,6 +760,9 @@ k_jacobi_tile(const __grid_constant__ CUtensorMap tm_u0, const __grid_constant__
         auto issue = [&](const Item& it, int stage, bool coef, bool flow) {   // lane 0 only
             unsigned char* st = smem + (size_t)stage * TS::STAGE;
             if (coef) {   // coefficient boxes are never written by a sweep launch
+                // the decoded item travels with its boxes: the compute warps read it after the full[]
+                // wait instead of each redoing the divisions (the arrive below releases this store)
+                reinterpret_cast<int4*>(smem + TS::OFF_INFO)[stage] = make_int4(it.x0, it.y0, it.b, it.p);
                 mbar_expect_tx(&full[stage], TS::TX_BYTES);
                 tma_load_3d(st + TS::OFF_CPK, &tm_cpk, &full[stage], it.x0, it.y0, it.b);
                 tma_load_3d(st + TS::OFF_INV, &tm_inv, &full[stage], it.x0, it.y0, it.b);
@@ -871,7 +875,6 @@ k_jacobi_tile(const __grid_constant__ CUtensorMap tm_u0, const __grid_constant__
     asm volatile("setmaxnreg.inc.sync.aligned.u32 152;");
     const int row0 = warp * R;                        // first tile row of this thread's patch
     for (int n = 0; n < items; ++n) {
-        const Item cur = item_of(n);
         const int stage = n & 1;
         unsigned char* st = smem + (size_t)stage * TS::STAGE;
         const float* s_u = reinterpret_cast<const float*>(st + TS::OFF_U);
@@ -879,7 +882,12 @@ k_jacobi_tile(const __grid_constant__ CUtensorMap tm_u0, const __grid_constant__
         const uint32_t* s_cpk = reinterpret_cast<const uint32_t*>(st + TS::OFF_CPK);
         const float* s_inv = reinterpret_cast<const float*>(st + TS::OFF_INV);
 
-        const int tx0 = cur.x0, ty0 = cur.y0, b = cur.b;
+        HS_PROF_T(pt0);
+        mbar_wait(&full[stage], (n >> 1) & 1);
+        HS_PROF_T(pt1);
+
+        const int4 info = reinterpret_cast<const int4*>(smem + TS::OFF_INFO)[stage];   // decoded by the producer
+        const int tx0 = info.x, ty0 = info.y, b = info.z, cur_p = info.w;
         const int gx0 = tx0 + lane * 4;
         const int gy0 = ty0 + row0;
         const bool tile_inside = (tx0 >= 0) && (tx0 + TS::SX <= g.W) && (ty0 >= 0) && (ty0 + TS::SY <= g.H);
@@ -895,10 +903,6 @@ k_jacobi_tile(const __grid_constant__ CUtensorMap tm_u0, const __grid_constant__
                     inmask |= (in ? 1u : 0u) << (j * 4 + c);
                 }
         }
-
-        HS_PROF_T(pt0);
-        mbar_wait(&full[stage], (n >> 1) & 1);
-        HS_PROF_T(pt1);
 
         float u[R][4], v[R][4], ix[R][4], iy[R][4], it[R][4], iv[R][4];
 #pragma unroll
@@ -937,7 +941,7 @@ k_jacobi_tile(const __grid_constant__ CUtensorMap tm_u0, const __grid_constant__
         HS_PROF_T(pt2);
 
         float* s_ex = reinterpret_cast<float*>(st);
-        const int kk = min(tg.k, tg.sweeps - cur.p * tg.k);
+        const int kk = min(tg.k, tg.sweeps - cur_p * tg.k);
         if (tile_inside)
             tile_sweeps<RL, RR, R, NWARP, false, TB>(u, v, ix, iy, it, iv, s_ex, kk, kf, warp, lane, inmask);
         else
@@ -947,8 +951,8 @@ k_jacobi_tile(const __grid_constant__ CUtensorMap tm_u0, const __grid_constant__
         // store the exact centre of the tile into the other pair of planes
         const int lx = lane * 4;
         if (lx >= tg.hxl && lx < tg.hxl + tg.vx && gx0 < g.W) {
-            float* U = ((cur.p & 1) ? u0 : u1) + (size_t)b * g.plane;
-            float* V = ((cur.p & 1) ? v0 : v1) + (size_t)b * g.plane;
+            float* U = ((cur_p & 1) ? u0 : u1) + (size_t)b * g.plane;
+            float* V = ((cur_p & 1) ? v0 : v1) + (size_t)b * g.plane;
 #pragma unroll
             for (int j = 0; j < R; ++j) {
                 const int ly = row0 + j;
