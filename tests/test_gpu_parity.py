@@ -202,7 +202,7 @@ def test_textbook_mode_matches_its_own_oracle(pkg, oracle, shape, iters, k):
     """SURVEY 8f row 4 (NOT a parity item): cube gradients + 1/6-1/12 weighted average, the scheme
     BASELINE.json's prose describes.  Checked against oracle.np_flow_textbook and fused == generic."""
     from cpp_optical_flow_b200 import hs_ctypes as H, synth
-    a, b = synth.frame_pair(shape[0], shape[1], seed=shape[0], shape=None) if False else synth.frame_pair(shape[0], shape[1], seed=shape[0])
+    a, b = synth.frame_pair(shape[0], shape[1], seed=shape[0])
     ogx, ogy, ogt, ou, ov = oracle.np_flow_textbook(a, b, iters, 1.0)
     with pkg.Solver(shape[1], shape[0], 3, iters, 1.0, temporal_k=k, flags=H.FLAG_TEXTBOOK) as s:
         gx, gy, gt = s.gradients(a, b)
