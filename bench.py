@@ -2,7 +2,7 @@
 """bench.py - Horn-Schunck Mpixel-iterations/s on B200 (BASELINE.json metric).
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
-                    [--workload 1080p|4k|kitti|slab16k] [--window 3|5] [--iters T] [--k K]
+                    [--workload 1080p|4k|kitti|batch256|slab16k] [--window 3|5] [--iters T] [--k K] [--textbook]
 
 A *step* is one complete solve of the workload: gradient/coefficient stage + T Jacobi sweeps.
   value  : whole-job Mpixel-iterations/s with the frames already resident in HBM
@@ -16,8 +16,10 @@ A *step* is one complete solve of the workload: gradient/coefficient stage + T J
            line-by-line cv2 restatement of hornSchunck.cpp - C++ OpenCV is not in this image, so
            hornSchunck.cpp itself cannot be compiled) on a bounded sample of the same workload.
 N > 1 (torchrun, one rank per GPU): the default workloads give every rank its own frame pair
-(BASELINE config 4: independent pairs, no communication, weak scaling); `slab16k` is the
-row-slab decomposition of one 16384^2 pair with halo exchange (config 5, strong scaling).
+(independent pairs, no communication, weak scaling); `batch256` deals the 256 pairs of BASELINE
+config 4 to the ranks (strong scaling); `slab16k` is the row-slab decomposition of one 16384^2
+pair with halo exchange (config 5, strong scaling).  `kitti` is config 1 on the reference's own
+bundled frame pair.
 """
 from __future__ import annotations
 
