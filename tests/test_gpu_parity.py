@@ -408,6 +408,21 @@ def test_config3_4k_crop_oracle(pkg, oracle):
         assert_flow_close(u[y0:y0 + 64, x0:x0 + 64], v[y0:y0 + 64, x0:x0 + 64], cu[sl], cv_[sl])
 
 
+def test_large_image_8192_square(pkg):
+    """Maximum-size style case (67 Mpixel, 1.7 GB of planes): fused == generic bit for bit, so no index
+    arithmetic overflows and the dataflow launch holds with 13 000 tiles per phase."""
+    from cpp_optical_flow_b200 import hs_ctypes as H
+    rng = np.random.default_rng(8192)
+    a = rng.integers(0, 256, (8192, 8192), dtype=np.uint8)
+    b = np.roll(a, 1, axis=1)
+    with pkg.Solver(8192, 8192, 3, 13, 1.0, flags=H.FLAG_FORCE_GENERIC) as s:
+        gu, gv = s.solve(a, b, np.float32)
+    with pkg.Solver(8192, 8192, 3, 13, 1.0) as s:
+        u, v = s.solve(a, b, np.float32)
+        assert s.timing().kernel_id == 1
+    assert np.array_equal(u, gu) and np.array_equal(v, gv)
+
+
 # ---------------------------------------------------------------- error behaviour
 def test_argument_errors(pkg):
     from cpp_optical_flow_b200 import hs_ctypes as H
