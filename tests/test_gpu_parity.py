@@ -250,7 +250,7 @@ def test_textbook_mode_needs_window_3(pkg):
 
 # ---------------------------------------------------------------- invariances (bit-exact)
 @pytest.mark.parametrize("w,k", [(3, 1), (3, 2), (3, 3), (3, 4), (3, 7), (3, 12), (5, 1), (5, 2), (5, 3), (5, 5),
-                                 (2, 4), (2, 9), (4, 2), (4, 3)])
+                                 (2, 4), (2, 9), (4, 2), (4, 3), (3, 10), (4, 5), (2, 12)])
 def test_fused_kernel_equals_generic_sweep(pkg, w, k):
     from cpp_optical_flow_b200 import hs_ctypes as H
     a, b = rand_pair((333, 517), seed=w * 10 + k)
@@ -261,6 +261,21 @@ def test_fused_kernel_equals_generic_sweep(pkg, w, k):
     with pkg.Solver(517, 333, w, iters, 1.0, temporal_k=k) as s:
         tu, tv = s.solve(a, b, np.float32)
         assert s.timing().kernel_id == 1 and s.timing().temporal_k == k
+    assert np.array_equal(gu, tu) and np.array_equal(gv, tv)
+
+
+@pytest.mark.parametrize("shape", [(40, 64), (375, 1242), (240, 320), (480, 640), (720, 1280)])
+@pytest.mark.parametrize("w", [3, 5])
+def test_default_k_on_small_frames(pkg, shape, w):
+    """Small frames pick their own k from a launch-cost model (hs_create); whatever it picks, the
+    result is the generic sweep's, bit for bit."""
+    from cpp_optical_flow_b200 import hs_ctypes as H
+    a, b = rand_pair(shape, seed=shape[0] + w)
+    with pkg.Solver(shape[1], shape[0], w, 37, 1.0, flags=H.FLAG_FORCE_GENERIC) as s:
+        gu, gv = s.solve(a, b, np.float32)
+    with pkg.Solver(shape[1], shape[0], w, 37, 1.0) as s:
+        tu, tv = s.solve(a, b, np.float32)
+        assert s.timing().kernel_id == 1 and 1 <= s.timing().temporal_k <= 12
     assert np.array_equal(gu, tu) and np.array_equal(gv, tv)
 
 
