@@ -564,13 +564,14 @@ int hs_create(const hs_config* cfg_in, hs_ctx** out) {
         cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
         c->multi_phase = coop && !c->top_seam && !c->bot_seam && !(cfg.flags & HS_FLAG_SINGLE_PHASE) &&
                          env_int("HS_SINGLE_PHASE", 0) == 0;
-        // The dataflow launch pays off when a phase is at least two rounds of tiles per SM: then a
-        // tile's inputs were published about a round before its turn.  With fewer tiles every
-        // phase is one dependent round and the publish/poll latency is exposed; plain launches
-        // chained by PDL are faster there (measured on the 1242x375 pair: 377 vs 275 Gpix-it/s).
+        // The dataflow launch pays off once a phase is more than about one round of tiles per SM: a
+        // tile's inputs are then published well before its turn.  With one round or less every
+        // phase is a dependent round and the publish/poll latency is exposed; plain launches
+        // chained by PDL are faster there (1242x375, 121 tiles: 377 vs 275 Gpix-it/s; 1280x720,
+        // 198..276 tiles: 354..506 vs 366..543, profiles/r01j_multi_phase_720p.txt).
         size_t tiles_k = 0;
         tile_dispatch(c, [&](auto t) { tiles_k = decltype(t)::tiles_for(c, c->k); });
-        if (tiles_k < (size_t)2 * c->num_sms && env_int("HS_MULTI_PHASE", 0) == 0) c->multi_phase = false;
+        if (tiles_k * 4 < (size_t)c->num_sms * 5 && env_int("HS_MULTI_PHASE", 0) == 0) c->multi_phase = false;
     }
     c->timing.temporal_k = c->k;
     c->timing.kernel_id = c->kernel_id;
