@@ -509,31 +509,37 @@ int hs_create(const hs_config* cfg_in, hs_ctx** out) {
         k = std::min(k, kmax);
         // keep a useful centre: at least a quarter of the staged rows must be output rows
         while (k > 1 && TS0::SY - (c->RL + c->RR) * k < TS0::SY / 4) --k;
-        // Small frames (less than two tiles per SM: one launch per phase, see multi_phase below) are
-        // paced by what a phase costs on top of its sweeps, and by whole waves of tiles: pick the k
-        // with the lowest modelled time per sweep,
-        //     (waves(k) * (k * t_sweep + t_tile) + t_launch) / k,     waves = ceil(tiles(k) / #SMs).
-        // The constants are microseconds measured on B200 (profiles/r01j_k_sweep_kitti.jsonl: the model
-        // is within 3 % of every point of that sweep); the k range is the one the parity tests cover.
+        // Small and medium frames (less than four tiles per SM) choose k from a cost model of a phase
+        // (microseconds, fitted on B200: profiles/r01j_k_sweep_kitti.jsonl, r01j_k_sweep_mid.jsonl):
+        //   a tile costs          item(k)  = k * t_sweep + t_tile
+        //   chained launches      phase(k) = ceil(tiles / #SMs) * item + t_launch     (tiles < 1.25 #SMs)
+        //   one dataflow launch   phase(k) = max(tiles / #SMs * item, item + t_dep)
+        // and the k with the lowest phase(k) / k wins.  t_dep is the publish -> poll -> fence -> TMA
+        // chain from a finished tile to its dependants: with few tiles per SM it, not the arithmetic,
+        // paces a phase, and fusing more sweeps per phase amortises it.  What matters in this regime
+        // is launches, whole waves and that chain, not the valid fraction of a staged tile.  The k
+        // range is the one the parity tests cover.  Larger frames keep the measured defaults above.
         const bool auto_k = cfg.temporal_k <= 0 && env_int("HS_K", 0) <= 0;
         if (auto_k && !c->top_seam && !c->bot_seam) {
             size_t n0 = 0;
             tile_dispatch(c, [&](auto t) { n0 = decltype(t)::tiles_for(c, k); });
-            if (n0 < (size_t)2 * c->num_sms) {
+            if (n0 < (size_t)4 * c->num_sms) {
                 const int rad = std::max(c->RL, c->RR);
-                const double t_sweep = rad <= 1 ? 0.59 : 0.97, t_tile = 1.5, t_launch = 2.4;
+                const double t_sweep = rad <= 1 ? 0.59 : 0.97, t_tile = 1.5, t_launch = 2.4, t_dep = 7.5;
                 int kcap = std::min(kmax, rad <= 1 ? 12 : 5);
                 if (cfg.max_iterations > 0) kcap = std::min(kcap, cfg.max_iterations);
+                const bool may_dataflow = !(cfg.flags & HS_FLAG_SINGLE_PHASE) && env_int("HS_SINGLE_PHASE", 0) == 0;
                 double best = 1e300;
                 for (int kk = 1; kk <= kcap; ++kk) {
                     if (kk > 1 && TS0::SY - (c->RL + c->RR) * kk < TS0::SY / 4) break;
                     size_t n = 0;
                     tile_dispatch(c, [&](auto t) { n = decltype(t)::tiles_for(c, kk); });
                     if (n == 0) break;
-                    if (n >= (size_t)2 * c->num_sms) continue;     // would leave the regime the model describes
-                    const double waves = (double)((n + c->num_sms - 1) / c->num_sms);
-                    const double cost = (waves * (kk * t_sweep + t_tile) + t_launch) / kk;
-                    if (cost < best) { best = cost; k = kk; }
+                    const double item = kk * t_sweep + t_tile;
+                    const bool dataflow = may_dataflow && n * 4 >= (size_t)c->num_sms * 5;
+                    const double phase = dataflow ? std::max((double)n / c->num_sms * item, item + t_dep)
+                                                  : (double)((n + c->num_sms - 1) / c->num_sms) * item + t_launch;
+                    if (phase / kk < best) { best = phase / kk; k = kk; }
                 }
             }
         }

@@ -4,7 +4,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import cpp_optical_flow_b200 as P
 from cpp_optical_flow_b200 import synth
-for (Hh, Ww) in [(240, 320), (375, 1242), (480, 640), (720, 1280), (1080, 1920)]:
+for (Hh, Ww) in [(240, 320), (375, 1242), (480, 640), (720, 1280), (768, 1366), (900, 1600), (1080, 1920), (1200, 1600), (1440, 2560)]:
     a, b = synth.frame_pair(Hh, Ww)
     for w in (3, 5):
         T = 1000
