@@ -246,6 +246,10 @@ def solve_slabs_single_process(prev, nxt, window, iterations, alpha, nslab, temp
     probe = Solver(W, max(H // nslab, 1), window, iterations, alpha, device=device, temporal_k=temporal_k)
     k = probe.timing().temporal_k
     probe.close()
+    # the library sizes its default k for a whole small frame; a slab must find k * depth sweeps'
+    # worth of halo rows inside its neighbour
+    while k > 1 and max(radii(window)) * k * depth > max(H // nslab, 1):
+        k -= 1
     geoms = [plan(H, W, nslab, r, window, k, depth) for r in range(nslab)]
     slabs = [DeviceSlab(g, iterations, alpha, device) for g in geoms]
     rl, rr = radii(window)
