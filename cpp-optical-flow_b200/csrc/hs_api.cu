@@ -159,6 +159,15 @@ struct Tile {
         return cudaFuncSetAttribute(kernel(), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TS::SMEM);
     }
     static int max_k() { return (TS::SY - 3) / std::max(1, RL + RR); }
+    // The multi-phase dataflow launch waits for the 3 x 3 adjacent tile counters only, so a staged
+    // tile must not reach past its direct neighbours: both halos have to fit inside one tile pitch.
+    // (w=5 from k=9, w=4 from k=10, w=3 from k=16 do not; those run as chained single-phase launches.)
+    static bool dataflow_ok(int k, int row_parity) {
+        const int hxl = round_up(RL * k, 4), hxr = round_up(RR * k, 4);
+        const int hyt = RL * k + ((row_parity + RL * k) & 1);
+        const int vx = TS::SX - hxl - hxr, vy = (TS::SY - hyt - RR * k) & ~1;
+        return vx > 0 && vy > 0 && hxl <= vx && hxr <= vx && hyt <= vy && RR * k <= vy;
+    }
     // One launch advances `sweeps` sweeps in phases of k.  phases > 1 needs every CTA resident at
     // once (they wait on each other's tiles) -> cooperative launch; a single phase is chained to
     // the previous launch with programmatic dependent launch instead.
@@ -178,6 +187,7 @@ struct Tile {
         tg.tiles_y = (row1 - row0 + tg.vy - 1) / tg.vy;
         tg.ntiles = tg.tiles_x * tg.tiles_y * c->B;
         const int phases = (sweeps + k - 1) / k;
+        if (phases > 1 && !dataflow_ok(k, row0 + c->grow0)) return cudaErrorInvalidValue;
         const int grid = std::min(tg.ntiles, c->num_sms);      // persistent: one CTA per SM
         const float kf = 1.0f / (float)(c->w * c->w);
         if (phases > 1) {
@@ -236,6 +246,10 @@ bool tile_dispatch(const hs_ctx* c, F&& f) {
     if (RL == 1 && RR == 1) { f(Tile<1, 1>{}); return true; }   // w = 3
     if (RL == 1 && RR == 2) { f(Tile<1, 2>{}); return true; }   // w = 4
     if (RL == 2 && RR == 2) { f(Tile<2, 2>{}); return true; }   // w = 5
+    if (RL == 2 && RR == 3) { f(Tile<2, 3>{}); return true; }   // w = 6
+    if (RL == 3 && RR == 3) { f(Tile<3, 3>{}); return true; }   // w = 7
+    if (RL == 3 && RR == 4) { f(Tile<3, 4>{}); return true; }   // w = 8
+    if (RL == 4 && RR == 4) { f(Tile<4, 4>{}); return true; }   // w = 9
     return false;
 }
 
@@ -504,7 +518,9 @@ int hs_create(const hs_config* cfg_in, hs_ctx** out) {
             // from HBM (fewer bytes per sweep) but k=4 when the 24 B/pixel working set sits in L2
             // (better valid fraction per staged tile); radius-2 windows k=3
             const bool l2_resident = (double)c->plane * c->B * 24.0 <= 64.0e6;
-            k = std::max(c->RL, c->RR) <= 1 ? (l2_resident ? 4 : 6) : 3;
+            // radius >= 3 (w = 6..9): the halo eats the 48-row stage quickly, k=2
+            const int rad = std::max(c->RL, c->RR);
+            k = rad <= 1 ? (l2_resident ? 4 : 6) : (rad == 2 ? 3 : 2);
         }
         k = std::min(k, kmax);
         // keep a useful centre: at least a quarter of the staged rows must be output rows
@@ -578,6 +594,11 @@ int hs_create(const hs_config* cfg_in, hs_ctx** out) {
         size_t tiles_k = 0;
         tile_dispatch(c, [&](auto t) { tiles_k = decltype(t)::tiles_for(c, c->k); });
         if (tiles_k * 4 < (size_t)c->num_sms * 5 && env_int("HS_MULTI_PHASE", 0) == 0) c->multi_phase = false;
+        // halos wider than one tile pitch (an explicit, very deep temporal_k): the 3 x 3 dependency
+        // rule of the dataflow launch would not cover them -> chained single-phase launches
+        bool df_ok = true;
+        tile_dispatch(c, [&](auto t) { df_ok = decltype(t)::dataflow_ok(c->k, c->oy0 + c->grow0); });
+        if (!df_ok) c->multi_phase = false;
     }
     c->timing.temporal_k = c->k;
     c->timing.kernel_id = c->kernel_id;
@@ -602,6 +623,8 @@ int hs_prepare(hs_ctx* c) {
 
 int hs_iterate(hs_ctx* c, int iterations) {
     if (!c) return HS_ERR_INVALID_ARG;
+    if ((c->top_seam || c->bot_seam) && iterations > c->k)
+        return fail(c, HS_ERR_UNSUPPORTED, "row-slab context: at most temporal_k=%d sweeps between halo refreshes", c->k);
     DevGuard g(c->dev);
     return do_iterate(c, iterations);
 }
@@ -656,6 +679,9 @@ int hs_iterate_until(hs_ctx* c, int max_sweeps, double tolerance, int check_ever
 
 int hs_solve_device(hs_ctx* c) {
     if (!c) return HS_ERR_INVALID_ARG;
+    if (c->top_seam || c->bot_seam)
+        return fail(c, HS_ERR_UNSUPPORTED, "hs_solve_device on a row-slab context: halos must be refreshed every "
+                                           "temporal_k sweeps (use hs_iterate / hs_iterate_rows or hs_slab_*)");
     DevGuard g(c->dev);
     c->timing.launches = 0;
     HS_CUDA(c, cudaEventRecord(c->ev[1], c->stream));
@@ -694,6 +720,9 @@ int hs_sync(hs_ctx* c) {
 int hs_solve(hs_ctx* c, const uint8_t* prev, size_t ps, size_t pis, const uint8_t* next, size_t ns, size_t nis,
              void* u, size_t us, size_t uis, void* v, size_t vs, size_t vis, int dt) {
     if (!c) return HS_ERR_INVALID_ARG;
+    if (c->top_seam || c->bot_seam)
+        return fail(c, HS_ERR_UNSUPPORTED, "hs_solve on a row-slab context: halos must be refreshed every temporal_k "
+                                           "sweeps (use hs_iterate / hs_iterate_rows or hs_slab_*)");
     DevGuard g(c->dev);
     c->timing.launches = 0;
     int rc;
@@ -922,13 +951,19 @@ extern "C" int hs_video_push(hs_ctx* c, const uint8_t* frame, size_t stride, voi
     int rc = video_setup(c, dt);
     if (rc) return rc;
     const int n = c->vid_frames;
+    // a flow is due whenever a pair is pending: check its destination BEFORE anything is queued, so a
+    // bad argument cannot cost the caller the pending pair
+    if (n >= 1 && c->vid_pending >= 0) {
+        const size_t es = dt == HS_F64 ? 8 : 4;
+        if (!u || !v) return fail(c, HS_ERR_INVALID_ARG, "null output pointer (the flow of pair %d is due)", c->vid_pending);
+        if (us < c->W * es || vs < c->W * es) return fail(c, HS_ERR_INVALID_ARG, "output row stride smaller than a row");
+    }
     // 1. upload frame n into ring slot n % 3 (last read by the gradient kernel of pair n-3)
     if (n >= 3) HS_CUDA(c, cudaStreamWaitEvent(c->copy_stream, c->ev_k1[(n - 3) % 3], 0));
     HS_CUDA(c, cudaMemcpy2DAsync(c->d_ring[n % 3], c->fpitch, frame, stride, c->W, c->H, cudaMemcpyHostToDevice,
                                  c->copy_stream));
     HS_CUDA(c, cudaEventRecord(c->ev_up, c->copy_stream));
-    c->vid_frames = n + 1;
-    if (n == 0) return HS_OK;
+    if (n == 0) { c->vid_frames = 1; return HS_OK; }
     // 2. queue the solve of pair p = (n-1, n) on the compute stream
     const int p = n - 1;
     const int prev_pending = c->vid_pending;
@@ -952,6 +987,7 @@ extern "C" int hs_video_push(hs_ctx* c, const uint8_t* frame, size_t stride, voi
         HS_CUDA(c, cudaMemcpyAsync(o + npx, c->d_v[c->cur], npx * sizeof(float), cudaMemcpyDeviceToDevice, c->stream));
     }
     HS_CUDA(c, cudaEventRecord(c->ev_solved[p & 1], c->stream));
+    c->vid_frames = n + 1;            // committed only now: a failed step above leaves the sequence where it was
     c->vid_pending = p;
     // 3. hand out the previous pair while this one is being solved
     if (prev_pending >= 0) {

@@ -67,7 +67,8 @@ typedef enum hs_dtype { HS_F32 = 0, HS_F64 = 1 } hs_dtype;
 /*
  * Replaces the three public fields + constructor of class hornSchunck (hornSchunck.cpp:10-17)
  * and adds the geometry the C++ code reads off cv::Mat.  Zero-initialise, set struct_size =
- * sizeof(hs_config), then fill what you need; 0 means "default" for every optional field.
+ * sizeof(hs_config), then fill what you need; 0 means "default" for every optional field except
+ * `device` (see there).
  */
 typedef struct hs_config {
     uint32_t struct_size;
@@ -77,7 +78,8 @@ typedef struct hs_config {
     int32_t max_iterations; /* maxIterations (:10,15), >= 0                            (required) */
     double alpha;           /* alpha (:11,16); 0 is legal and yields IEEE nan/inf like upstream   */
     int32_t batch;          /* independent frame pairs solved per call (default 1)                */
-    int32_t device;         /* CUDA ordinal; -1 = current device                                  */
+    int32_t device;         /* CUDA ordinal.  NOTE: 0 is ordinal 0, not "default" - a zero-initialised
+                               config binds to device 0; pass -1 for the calling thread's current device */
     int32_t temporal_k;     /* sweeps fused per phase (temporal blocking depth k); 0 = auto       */
     uint32_t flags;         /* HS_FLAG_*                                                          */
     /* Row-slab decomposition (one context per GPU).  The context's buffer holds `height` rows of

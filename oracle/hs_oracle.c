@@ -56,56 +56,103 @@ static inline int reflect101(int i, int n) {
         }                                                                                          \
     }                                                                                              \
                                                                                                    \
-    /* one filter2D(BORDER_CONSTANT) pass, :60-61.  `pad` is a zeroed (H+w-1) x (W+w-1) scratch  */    \
-    /* plane: the image is copied to its centre, so out-of-image taps read 0 (= BORDER_CONSTANT)   */    \
-    /* and every pixel still accumulates kf*tap in dy-major / dx-minor order.                      */    \
-    static void box_##SUF(const REAL* restrict f, REAL* restrict out, REAL* restrict pad, int H, int W, int w) {              \
-        const int a = w - w / 2 - 1;                                             /* :54 */         \
-        const REAL kf = (REAL)1 / (REAL)(w * w);                                 /* :53 */         \
-        const size_t PW = (size_t)W + w - 1;                                                       \
-        _Pragma("omp parallel for schedule(static)")                                               \
-        for (int y = 0; y < H; ++y)                                                                \
-            memcpy(pad + (size_t)(y + a) * PW + a, f + (size_t)y * W, (size_t)W * sizeof(REAL));   \
+    /* Gradients of frames that are already REAL (the reference converts ANY input depth with    */    \
+    /* convertTo(CV_64FC1) first, :23-24; for 8-bit frames this gives the same values as above). */    \
+    void hs_oracle_gradients_real_##SUF(const REAL* prev, const REAL* next, int H, int W,          \
+                                        REAL* gx, REAL* gy, REAL* gt) {                            \
         _Pragma("omp parallel for schedule(static)")                                               \
         for (int y = 0; y < H; ++y) {                                                              \
-            REAL* restrict o = out + (size_t)y * W;                                                    \
-            for (int x = 0; x < W; ++x) o[x] = 0;                                                  \
-            for (int dy = 0; dy < w; ++dy) {                                                       \
-                const REAL* restrict r = pad + (size_t)(y + dy) * PW;                                    \
-                for (int dx = 0; dx < w; ++dx)                                                     \
-                    for (int x = 0; x < W; ++x) o[x] += kf * r[x + dx];                            \
+            const REAL* r0 = prev + (size_t)reflect101(y - 1, H) * W;                              \
+            const REAL* r1 = prev + (size_t)y * W;                                                 \
+            const REAL* r2 = prev + (size_t)reflect101(y + 1, H) * W;                              \
+            for (int x = 0; x < W; ++x) {                                                          \
+                int xm = reflect101(x - 1, W), xp = reflect101(x + 1, W);                          \
+                REAL a = r0[xm], b = r0[x], c = r0[xp];                                            \
+                REAL d = r1[xm], f = r1[xp];                                                       \
+                REAL g = r2[xm], h = r2[x], i = r2[xp];                                            \
+                size_t o = (size_t)y * W + x;                                                      \
+                gx[o] = (c + (REAL)2 * f + i) - (a + (REAL)2 * d + g);           /* :27 */         \
+                gy[o] = (g + (REAL)2 * h + i) - (a + (REAL)2 * b + c);           /* :28 */         \
+                gt[o] = next[o] - r1[x];                                         /* :39 */         \
             }                                                                                      \
         }                                                                                          \
+    }                                                                                              \
+                                                                                                   \
+    /* The T sweeps of :56-74 on given gradient planes.  u and v live in zero-bordered planes of  */    \
+    /* (H+w-1) x (W+w-1) (image at offset (a, a)), so out-of-image taps read 0 = BORDER_CONSTANT  */    \
+    /* (:60-61); two such pairs ping-pong.  One pass per sweep and row: both box means (every     */    \
+    /* tap multiplied by kf = fl(1/w^2) and accumulated dy-major / dx-minor, exactly the order of */    \
+    /* the NumPy twin and of cv2.filter2D for w <= 7), then the update :63-73.                    */    \
+    static int sweeps_##SUF(const REAL* gx, const REAL* gy, const REAL* gt, int H, int W, int w,   \
+                            int iters, double alpha, REAL* u, REAL* v) {                           \
+        const size_t n = (size_t)H * W;                                                            \
+        const int a = w - w / 2 - 1;                                             /* :54 */         \
+        const REAL kf = (REAL)1 / (REAL)(w * w);                                 /* :53 */         \
+        const size_t PW = (size_t)W + w - 1, PH = (size_t)H + w - 1;                               \
+        REAL* buf = (REAL*)calloc(4 * PW * PH + n, sizeof(REAL));                /* :49-50 */      \
+        if (!buf) return -1;                                                                       \
+        REAL* pu[2] = {buf, buf + PW * PH};                                                        \
+        REAL* pv[2] = {buf + 2 * PW * PH, buf + 3 * PW * PH};                                      \
+        REAL* den = buf + 4 * PW * PH;                                                             \
+        const REAL a2 = (REAL)alpha * (REAL)alpha;                                                 \
+        for (size_t i = 0; i < n; ++i) den[i] = a2 + gx[i] * gx[i] + gy[i] * gy[i];  /* :65-66,68 */ \
+        int cur = 0;                                                                               \
+        for (int it = 0; it < iters; ++it, cur ^= 1) {                           /* :56 */         \
+            const REAL* restrict su = pu[cur];                                                     \
+            const REAL* restrict sv = pv[cur];                                                     \
+            REAL* restrict du = pu[cur ^ 1];                                                       \
+            REAL* restrict dv = pv[cur ^ 1];                                                       \
+            _Pragma("omp parallel for schedule(static)")                                           \
+            for (int y = 0; y < H; ++y) {                                                          \
+                REAL ua[W], va[W];                                                                 \
+                for (int x = 0; x < W; ++x) ua[x] = va[x] = 0;                                     \
+                for (int dy = 0; dy < w; ++dy) {                                                   \
+                    const REAL* restrict ru = su + (size_t)(y + dy) * PW;                          \
+                    const REAL* restrict rv = sv + (size_t)(y + dy) * PW;                          \
+                    for (int dx = 0; dx < w; ++dx)                                                 \
+                        for (int x = 0; x < W; ++x) {                                              \
+                            ua[x] += kf * ru[x + dx];                            /* :60 */         \
+                            va[x] += kf * rv[x + dx];                            /* :61 */         \
+                        }                                                                          \
+                }                                                                                  \
+                const size_t o = (size_t)y * W, po = (size_t)(y + a) * PW + a;                     \
+                for (int x = 0; x < W; ++x) {                                                      \
+                    REAL c = (gx[o + x] * ua[x] + gy[o + x] * va[x] + gt[o + x]) / den[o + x]; /* :63-68 */ \
+                    du[po + x] = ua[x] - gx[o + x] * c;                          /* :69,72 */      \
+                    dv[po + x] = va[x] - gy[o + x] * c;                          /* :70,73 */      \
+                }                                                                                  \
+            }                                                                                      \
+        }                                                                                          \
+        for (int y = 0; y < H; ++y) {                                                              \
+            memcpy(u + (size_t)y * W, pu[cur] + (size_t)(y + a) * PW + a, (size_t)W * sizeof(REAL)); \
+            memcpy(v + (size_t)y * W, pv[cur] + (size_t)(y + a) * PW + a, (size_t)W * sizeof(REAL)); \
+        }                                                                                          \
+        free(buf);                                                                                 \
+        return 0;                                                                                  \
     }                                                                                              \
                                                                                                    \
     /* hornSchunck.cpp:43-75.  u, v: H*W outputs.  Returns 0, or -1 if out of memory. */           \
     int hs_oracle_flow_##SUF(const uint8_t* prev, const uint8_t* next, int H, int W, int w,        \
                              int iters, double alpha, REAL* u, REAL* v) {                          \
         size_t n = (size_t)H * W;                                                                  \
-        size_t np_ = ((size_t)H + w - 1) * ((size_t)W + w - 1);                                    \
-        REAL* buf = (REAL*)malloc((n * 6 + np_) * sizeof(REAL));                                   \
-        if (!buf) return -1;                                                                       \
-        REAL* pad = buf + 6 * n;                                                                   \
-        memset(pad, 0, np_ * sizeof(REAL));                                                        \
-        REAL *gx = buf, *gy = buf + n, *gt = buf + 2 * n, *den = buf + 3 * n;                      \
-        REAL *ua = buf + 4 * n, *va = buf + 5 * n;                                                 \
-        hs_oracle_gradients_##SUF(prev, next, H, W, gx, gy, gt);                 /* :46 */         \
-        memset(u, 0, n * sizeof(REAL));                                          /* :49 */         \
-        memset(v, 0, n * sizeof(REAL));                                          /* :50 */         \
-        const REAL a2 = (REAL)alpha * (REAL)alpha;                                                 \
-        for (size_t i = 0; i < n; ++i) den[i] = a2 + gx[i] * gx[i] + gy[i] * gy[i];                \
-        for (int it = 0; it < iters; ++it) {                                     /* :56 */         \
-            box_##SUF(u, ua, pad, H, W, w);                                          /* :60 */         \
-            box_##SUF(v, va, pad, H, W, w);                                          /* :61 */         \
-            _Pragma("omp parallel for schedule(static)")                                           \
-            for (size_t i = 0; i < n; ++i) {                                                       \
-                REAL c = (gx[i] * ua[i] + gy[i] * va[i] + gt[i]) / den[i];       /* :63-68 */      \
-                u[i] = ua[i] - gx[i] * c;                                        /* :69,72 */      \
-                v[i] = va[i] - gy[i] * c;                                        /* :70,73 */      \
-            }                                                                                      \
-        }                                                                                          \
-        free(buf);                                                                                 \
-        return 0;                                                                                  \
+        REAL* g = (REAL*)malloc(3 * n * sizeof(REAL));                                             \
+        if (!g) return -1;                                                                         \
+        hs_oracle_gradients_##SUF(prev, next, H, W, g, g + n, g + 2 * n);        /* :46 */         \
+        int rc = sweeps_##SUF(g, g + n, g + 2 * n, H, W, w, iters, alpha, u, v);                   \
+        free(g);                                                                                   \
+        return rc;                                                                                 \
+    }                                                                                              \
+                                                                                                   \
+    /* the same for frames of any depth, already converted to REAL as :23-24 does */               \
+    int hs_oracle_flow_real_##SUF(const REAL* prev, const REAL* next, int H, int W, int w,         \
+                                  int iters, double alpha, REAL* u, REAL* v) {                     \
+        size_t n = (size_t)H * W;                                                                  \
+        REAL* g = (REAL*)malloc(3 * n * sizeof(REAL));                                             \
+        if (!g) return -1;                                                                         \
+        hs_oracle_gradients_real_##SUF(prev, next, H, W, g, g + n, g + 2 * n);                     \
+        int rc = sweeps_##SUF(g, g + n, g + 2 * n, H, W, w, iters, alpha, u, v);                   \
+        free(g);                                                                                   \
+        return rc;                                                                                 \
     }
 
 DEFINE_ORACLE(f64, double)

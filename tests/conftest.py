@@ -47,11 +47,25 @@ def c_oracle():
             h, wd = prev.shape
             u = np.zeros((h, wd), dtype)
             v = np.zeros((h, wd), dtype)
-            lib.hs_oracle_set_threads(int(threads) if threads else 1)   # 1 thread: vCPUs here do not scale
+            # OpenMP over rows (bit-identical for any thread count: every pixel is summed by one thread)
+            lib.hs_oracle_set_threads(int(threads) if threads else min(os.cpu_count() or 1, 32))
             fn = lib.hs_oracle_flow_f64 if np.dtype(dtype) == np.float64 else lib.hs_oracle_flow_f32
             vp = ctypes.c_void_p
             rc = fn(vp(prev.ctypes.data), vp(nxt.ctypes.data), h, wd, int(w), int(iters),
                     ctypes.c_double(alpha), vp(u.ctypes.data), vp(v.ctypes.data))
+            assert rc == 0
+            return u, v
+
+        def flow_real(self, prev, nxt, w, iters, alpha, threads=0):
+            """Frames of any depth, converted to float64 first as hornSchunck.cpp:23-24 does."""
+            prev = np.ascontiguousarray(prev, np.float64)
+            nxt = np.ascontiguousarray(nxt, np.float64)
+            h, wd = prev.shape
+            u = np.zeros((h, wd)); v = np.zeros((h, wd))
+            lib.hs_oracle_set_threads(int(threads) if threads else min(os.cpu_count() or 1, 32))
+            vp = ctypes.c_void_p
+            rc = lib.hs_oracle_flow_real_f64(vp(prev.ctypes.data), vp(nxt.ctypes.data), h, wd, int(w), int(iters),
+                                             ctypes.c_double(alpha), vp(u.ctypes.data), vp(v.ctypes.data))
             assert rc == 0
             return u, v
 
@@ -86,3 +100,19 @@ def kitti():
 def pkg():
     import cpp_optical_flow_b200
     return cpp_optical_flow_b200
+
+
+@pytest.fixture(scope="session")
+def record():
+    """Append measured parity deltas to gpurun_out/parity_deltas.jsonl (read back into DESIGN.md)."""
+    import json
+    path = os.path.join(ROOT, "gpurun_out", "parity_deltas.jsonl")
+
+    def rec(**kw):
+        try:
+            os.makedirs(os.path.dirname(path), exist_ok=True)
+            with open(path, "a") as f:
+                f.write(json.dumps(kw) + "\n")
+        except OSError:
+            pass
+    return rec

@@ -68,7 +68,7 @@ def test_gradients_bit_exact_kitti(pkg, oracle, kitti, pair):
 
 
 # ---------------------------------------------------------------- flow (getFlow :43-75)
-@pytest.mark.parametrize("w", [1, 2, 3, 4, 5, 7, 8])
+@pytest.mark.parametrize("w", [1, 2, 3, 4, 5, 6, 7, 8, 9, 11])
 @pytest.mark.parametrize("alpha", [0.5, 1.0, 10.0])
 @pytest.mark.parametrize("iters", [1, 2, 7, 100])
 def test_flow_matches_oracle(pkg, c_oracle, w, alpha, iters):
@@ -250,7 +250,11 @@ def test_textbook_mode_needs_window_3(pkg):
 
 # ---------------------------------------------------------------- invariances (bit-exact)
 @pytest.mark.parametrize("w,k", [(3, 1), (3, 2), (3, 3), (3, 4), (3, 7), (3, 12), (5, 1), (5, 2), (5, 3), (5, 5),
-                                 (2, 4), (2, 9), (4, 2), (4, 3), (3, 10), (4, 5), (2, 12)])
+                                 (2, 4), (2, 9), (4, 2), (4, 3), (3, 10), (4, 5), (2, 12),
+                                 (6, 1), (6, 2), (6, 3), (7, 1), (7, 2), (7, 3), (8, 1), (8, 2), (8, 3), (9, 1), (9, 2),
+                                 # deepest k per window: beyond what the dataflow launch's 3x3 dependency rule
+                                 # covers, so these must fall back to chained single-phase launches
+                                 (3, 15), (3, 18), (4, 10), (4, 12), (5, 8), (5, 9), (7, 5), (9, 4)])
 def test_fused_kernel_equals_generic_sweep(pkg, w, k):
     from cpp_optical_flow_b200 import hs_ctypes as H
     a, b = rand_pair((333, 517), seed=w * 10 + k)
@@ -436,6 +440,57 @@ def test_large_image_8192_square(pkg):
         u, v = s.solve(a, b, np.float32)
         assert s.timing().kernel_id == 1
     assert np.array_equal(u, gu) and np.array_equal(v, gv)
+
+
+# ---------------------------------------------------------------- oracle parity AT THE DEPTH the configs name
+def deltas(u, v, ou, ov):
+    du, dv = float(np.abs(u - ou).max()), float(np.abs(v - ov).max())
+    epe = float(np.abs(np.hypot(u, v) - np.hypot(ou, ov)).mean())
+    return du, dv, epe
+
+
+@pytest.mark.parametrize("w", [3, 5])
+def test_config2_1080p_1000_sweeps_vs_fp64_oracle(pkg, c_oracle, record, w):
+    """configs[1] exactly: 1920x1080, alpha=1, 1000 sweeps (hornSchunck.cpp:56-74), hs_solve against the
+    fp64 C oracle at full size and full depth (oracle: ~2 G pixel-iterations, OpenMP over rows)."""
+    from cpp_optical_flow_b200 import synth
+    a, b = synth.frame_pair(1080, 1920)
+    ou, ov = c_oracle.flow(a, b, w, 1000, 1.0)
+    with pkg.Solver(1920, 1080, w, 1000, 1.0) as s:
+        u, v = s.solve(a, b, np.float64)
+        k = s.timing().temporal_k
+    du, dv, epe = deltas(u, v, ou, ov)
+    record(case=f"1080p w={w} T=1000", k=k, max_du=du, max_dv=dv, epe=epe, umax=float(np.abs(ou).max()))
+    assert du <= TOL_MAX and dv <= TOL_MAX and epe <= TOL_EPE, f"max|du|={du:.3e} max|dv|={dv:.3e} mean EPE diff={epe:.3e}"
+
+
+@pytest.mark.parametrize("pair", ["000050", "000040"])
+def test_kitti_w3_1000_sweeps_vs_fp64_oracle(pkg, c_oracle, record, kitti, pair):
+    """The fp32 worst case SURVEY found (real images, |u| > 100 px, w=3, 1000 sweeps: 7.5e-5 with a
+    different summation order).  Full fp64 oracle."""
+    a, b = kitti(pair)
+    ou, ov = c_oracle.flow(a, b, 3, 1000, 1.0)
+    with pkg.Solver(a.shape[1], a.shape[0], 3, 1000, 1.0) as s:
+        u, v = s.solve(a, b, np.float64)
+        k = s.timing().temporal_k
+    du, dv, epe = deltas(u, v, ou, ov)
+    record(case=f"kitti {pair} w=3 T=1000", k=k, max_du=du, max_dv=dv, epe=epe, umax=float(np.abs(ou).max()))
+    assert np.abs(ou).max() > 50
+    assert du <= TOL_MAX and dv <= TOL_MAX and epe <= TOL_EPE, f"max|du|={du:.3e} max|dv|={dv:.3e} mean EPE diff={epe:.3e}"
+
+
+def test_config3_4k_2000_sweeps_vs_fp64_oracle(pkg, c_oracle, record):
+    """configs[2] exactly: 3840x2160, 2000 sweeps, against the full fp64 C oracle (16.6 G pixel-iterations;
+    about a minute on the GPU box's host cores)."""
+    from cpp_optical_flow_b200 import synth
+    a, b = synth.frame_pair(2160, 3840)
+    ou, ov = c_oracle.flow(a, b, 3, 2000, 1.0)
+    with pkg.Solver(3840, 2160, 3, 2000, 1.0) as s:
+        u, v = s.solve(a, b, np.float64)
+        k = s.timing().temporal_k
+    du, dv, epe = deltas(u, v, ou, ov)
+    record(case="4k w=3 T=2000", k=k, max_du=du, max_dv=dv, epe=epe, umax=float(np.abs(ou).max()))
+    assert du <= TOL_MAX and dv <= TOL_MAX and epe <= TOL_EPE, f"max|du|={du:.3e} max|dv|={dv:.3e} mean EPE diff={epe:.3e}"
 
 
 # ---------------------------------------------------------------- error behaviour
