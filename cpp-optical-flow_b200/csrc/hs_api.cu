@@ -12,6 +12,7 @@
 #include <cstring>
 #include <new>
 #include <string>
+#include <vector>
 
 #include "hs_kernels.cuh"
 
@@ -79,6 +80,35 @@ struct hs_ctx {
     size_t bgr_pitch = 0;
 
     CUtensorMap tm_u[2], tm_v[2], tm_cpk, tm_inv;
+    // Row-slab seams (multi-GPU): where each neighbouring slab lives.  Set by slab_link(); a linked
+    // context runs all sweeps of hs_iterate in ONE launch and exchanges halos from inside the kernel.
+    struct Seam {
+        bool on = false;
+        float* u[2] = {nullptr, nullptr};   // the neighbour's planes (peer-mapped device memory)
+        float* v[2] = {nullptr, nullptr};
+        int dy = 0;                         // my buffer row y is the neighbour's buffer row y + dy
+        int* inbox = nullptr;               // the neighbour's inbox (it polls it; my seam tiles publish there)
+        int nbr_rows = 0, nbr_parity = 0;   // the neighbour's produced rows and the image-row parity of its first one
+    };
+    Seam up, dn;
+    int* d_inbox = nullptr;      // [2][SEAM_JMAX][tiles_x]: phase counts published by the neighbours
+    void* arena = nullptr;       // seam contexts: u[2], v[2] and the inbox live in ONE allocation (one IPC handle)
+    size_t arena_bytes = 0, inbox_off = 0, plane_off[4] = {0, 0, 0, 0};
+    void* ipc_up = nullptr;      // arenas of the neighbours opened with cudaIpcOpenMemHandle (multi-process)
+    void* ipc_dn = nullptr;
+    bool linked = false;
+    int reverse = 0;             // walk tile rows bottom-up (odd slabs)
+    // row-slab geometry inside the full image (slab_world > 1 contexts and children of a row-slab group)
+    int slab_rank = 0, slab_world = 1, img_h = 0;
+    int sl_y0 = 0, sl_y1 = 0, sl_b0 = 0, sl_b1 = 0, sl_f0 = 0, sl_f1 = 0;
+    // several GPUs behind one context (hs_config.num_devices > 1): the children, one per device
+    std::vector<hs_ctx*> kids;
+    int decomp = 0, exchange = 0;
+    bool emulate = false;        // all children on ONE device: their slabs run in a single launch
+    cudaEvent_t ev_x = nullptr;  // child: "my last prepare / iterate is done" for the neighbours' streams
+    struct NcclState* nccl = nullptr;
+    int phase_count = 0;         // phases completed since hs_prepare
+    int max_ctas = 0;            // 0 = one CTA per SM
     int kernel_id = 0;  // 0 generic, 1 fused tile
     int num_sms = 148;
     bool use_pdl = true;
@@ -151,48 +181,128 @@ int env_int(const char* name, int dflt) {
     return (s && *s) ? atoi(s) : dflt;
 }
 
+constexpr int EMU_MAXS = 4;     // row slabs of ONE device that a single (emulation) launch can hold
+
+// tile-row geometry of `rows` produced rows whose first row has image-row parity `parity`
+struct RowTiling {
+    int hyt, vy, tiles_y, jt, jb;
+};
+
 template <int RL, int RR, bool TB = false>
 struct Tile {
     using TS = hs::TileShape<RL, RR, TILE_R, TILE_NWARP>;
-    static auto kernel() { return hs::k_jacobi_tile<RL, RR, TILE_R, TILE_NWARP, TB>; }
+    template <int MAXS>
+    static auto kernel() { return hs::k_jacobi_tile<RL, RR, TILE_R, TILE_NWARP, TB, MAXS>; }
     static cudaError_t configure() {
-        return cudaFuncSetAttribute(kernel(), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TS::SMEM);
+        cudaError_t e = cudaFuncSetAttribute(kernel<1>(), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TS::SMEM);
+        if (e == cudaSuccess)
+            e = cudaFuncSetAttribute(kernel<EMU_MAXS>(), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TS::SMEM);
+        return e;
     }
     static int max_k() { return (TS::SY - 3) / std::max(1, RL + RR); }
+    // every staged tile must start on an EVEN image row (the canonical column sums pair rows
+    // (2i, 2i+1), and a thread's 4-row patch shares those pair sums): one more halo row above
+    // when needed, and an even tile pitch
+    static RowTiling tiling(int k, int rows, int parity) {
+        RowTiling t;
+        t.hyt = RL * k + ((parity + RL * k) & 1);
+        t.vy = (TS::SY - t.hyt - RR * k) & ~1;
+        if (t.vy <= 0) { t.tiles_y = 0; t.jt = t.jb = 0; return t; }
+        t.tiles_y = (rows + t.vy - 1) / t.vy;
+        // tile rows whose stored centre lies within max(RL, RR) * k rows of the slab's first / last row:
+        // they read the neighbouring slab's rows and produce the rows it reads
+        const int reach = std::max(RL, RR) * k;
+        t.jt = std::min(t.tiles_y, (reach + t.vy - 1) / t.vy);
+        t.jb = t.tiles_y - std::max(rows - reach, 0) / t.vy;
+        return t;
+    }
+    static int vx_of(int k) { return TS::SX - round_up(RL * k, 4) - round_up(RR * k, 4); }
     // The multi-phase dataflow launch waits for the 3 x 3 adjacent tile counters only, so a staged
     // tile must not reach past its direct neighbours: both halos have to fit inside one tile pitch.
     // (w=5 from k=9, w=4 from k=10, w=3 from k=16 do not; those run as chained single-phase launches.)
     static bool dataflow_ok(int k, int row_parity) {
         const int hxl = round_up(RL * k, 4), hxr = round_up(RR * k, 4);
-        const int hyt = RL * k + ((row_parity + RL * k) & 1);
-        const int vx = TS::SX - hxl - hxr, vy = (TS::SY - hyt - RR * k) & ~1;
-        return vx > 0 && vy > 0 && hxl <= vx && hxr <= vx && hyt <= vy && RR * k <= vy;
+        const RowTiling t = tiling(k, 1 << 20, row_parity);
+        const int vx = vx_of(k);
+        return vx > 0 && t.vy > 0 && hxl <= vx && hxr <= vx && t.hyt <= t.vy && RR * k <= t.vy;
     }
-    // One launch advances `sweeps` sweeps in phases of k.  phases > 1 needs every CTA resident at
-    // once (they wait on each other's tiles) -> cooperative launch; a single phase is chained to
+    // Describe what context c contributes to a launch that produces its rows [row0, row1).
+    static bool fill_slab(const hs_ctx* c, hs::SlabDesc& S, int k, int row0, int row1, int tile0, bool seams) {
+        memset(&S, 0, sizeof S);
+        for (int i = 0; i < 2; ++i) {
+            S.tm_u[i] = c->tm_u[i]; S.tm_v[i] = c->tm_v[i];
+            S.u[i] = c->d_u[i]; S.v[i] = c->d_v[i];
+        }
+        S.tm_cpk = c->tm_cpk; S.tm_inv = c->tm_inv;
+        S.g = c->geom();
+        S.g.oy0 = row0;                                        // rows this launch produces
+        S.g.oy1 = row1;
+        const RowTiling t = tiling(k, row1 - row0, row0 + c->grow0);
+        const int vx = vx_of(k);
+        if (vx <= 0 || t.vy <= 0) return false;
+        S.hyt = t.hyt; S.vy = t.vy; S.tiles_y = t.tiles_y;
+        const int tiles_x = (c->W + vx - 1) / vx;
+        S.ntiles = tiles_x * t.tiles_y * c->B;
+        S.tile0 = tile0;
+        S.fd_per_img = hs::FastDiv::make((uint32_t)(tiles_x * t.tiles_y));
+        S.jt = t.jt; S.jb = t.jb;
+        if (seams) {
+            if (t.jt > hs::SEAM_JMAX || t.jb > hs::SEAM_JMAX) return false;
+            S.reverse = c->reverse;
+            S.inbox = c->d_inbox;
+            const hs_ctx::Seam* side[2] = {&c->up, &c->dn};
+            for (int q = 0; q < 2; ++q) {
+                const hs_ctx::Seam& L = *side[q];
+                if (!L.on) continue;
+                const RowTiling nt = tiling(k, L.nbr_rows, L.nbr_parity);
+                if (nt.vy != t.vy || nt.jt > hs::SEAM_JMAX || nt.jb > hs::SEAM_JMAX) return false;   // tile columns AND pitch must agree
+                if (q == 0) {
+                    for (int i = 0; i < 2; ++i) { S.up_u[i] = L.u[i]; S.up_v[i] = L.v[i]; }
+                    S.up_dy = L.dy; S.push_up = RR * k; S.up_j = nt.jb;
+                    S.out_up = L.inbox + (size_t)1 * hs::SEAM_JMAX * tiles_x;   // I am "the slab below" for it
+                } else {
+                    for (int i = 0; i < 2; ++i) { S.dn_u[i] = L.u[i]; S.dn_v[i] = L.v[i]; }
+                    S.dn_dy = L.dy; S.push_dn = RL * k; S.dn_j = nt.jt;
+                    S.out_dn = L.inbox;                                          // I am "the slab above" for it
+                }
+            }
+        }
+        return true;
+    }
+    // One launch advances `sweeps` sweeps in phases of k on n contexts of ONE device (n == 1 except for
+    // the single-device emulation of row slabs).  phases > 1 - or any seam - needs every CTA resident
+    // at once (they wait on each other's tiles) -> cooperative launch; a single phase is chained to
     // the previous launch with programmatic dependent launch instead.
-    static cudaError_t launch(hs_ctx* c, int k, int sweeps, int row0, int row1) {
-        hs::TileGrid tg;
-        tg.k = k;
-        tg.sweeps = sweeps;
-        tg.hxl = round_up(RL * k, 4);
-        tg.vx = TS::SX - tg.hxl - round_up(RR * k, 4);
-        // every staged tile must start on an EVEN image row (the canonical column sums pair rows
-        // (2i, 2i+1), and a thread's 4-row patch shares those pair sums): one more halo row above
-        // when needed, and an even tile pitch
-        tg.hyt = RL * k + ((row0 + c->grow0 + RL * k) & 1);
-        tg.vy = (TS::SY - tg.hyt - RR * k) & ~1;
-        if (tg.vx <= 0 || tg.vy <= 0) return cudaErrorInvalidValue;
-        tg.tiles_x = (c->W + tg.vx - 1) / tg.vx;
-        tg.tiles_y = (row1 - row0 + tg.vy - 1) / tg.vy;
-        tg.ntiles = tg.tiles_x * tg.tiles_y * c->B;
+    template <int MAXS>
+    static cudaError_t launch_n(hs_ctx* const* cs, int n, int k, int sweeps, int row0, int row1, bool seams) {
+        hs_ctx* c = cs[0];
+        hs::LaunchDesc<MAXS> d;
+        memset(&d, 0, sizeof d);
+        int total = 0;
+        for (int i = 0; i < n; ++i) {
+            const int r0 = n == 1 ? row0 : cs[i]->oy0, r1 = n == 1 ? row1 : cs[i]->oy1;
+            if (!fill_slab(cs[i], d.s[i], k, r0, r1, total, seams)) return cudaErrorInvalidValue;
+            total += d.s[i].ntiles;
+        }
+        d.nslabs = n; d.k = k; d.sweeps = sweeps; d.cur = c->cur; d.phase_base = c->phase_count;
+        d.hxl = round_up(RL * k, 4);
+        d.vx = vx_of(k);
+        d.tiles_x = (c->W + d.vx - 1) / d.vx;
+        d.fd_tiles_x = hs::FastDiv::make((uint32_t)d.tiles_x);
+        d.ntiles = total;
+        d.done = c->d_done;
+        d.kf = 1.0f / (float)(c->w * c->w);
+        d.alpha2 = (float)(c->alpha * c->alpha);
         const int phases = (sweeps + k - 1) / k;
+        bool any_seam = false;
+        for (int i = 0; i < n; ++i) any_seam |= d.s[i].out_up || d.s[i].out_dn || d.s[i].up_j || d.s[i].dn_j;
         if (phases > 1 && !dataflow_ok(k, row0 + c->grow0)) return cudaErrorInvalidValue;
-        const int grid = std::min(tg.ntiles, c->num_sms);      // persistent: one CTA per SM
-        const float kf = 1.0f / (float)(c->w * c->w);
-        if (phases > 1) {
-            if ((size_t)tg.ntiles > c->done_cap) return cudaErrorInvalidValue;
-            cudaError_t e = cudaMemsetAsync(c->d_done, 0, (size_t)tg.ntiles * sizeof(int), c->stream);
+        if (any_seam && !dataflow_ok(k, row0 + c->grow0)) return cudaErrorInvalidValue;
+        int grid = std::min(total, c->num_sms);                // persistent: one CTA per SM
+        if (c->max_ctas > 0) grid = std::min(grid, c->max_ctas);
+        if (phases > 1 || any_seam) {
+            if ((size_t)total > c->done_cap) return cudaErrorInvalidValue;
+            cudaError_t e = cudaMemsetAsync(c->d_done, 0, (size_t)total * sizeof(int), c->stream);
             if (e != cudaSuccess) return e;
         }
         cudaLaunchConfig_t cfg = {};
@@ -201,7 +311,7 @@ struct Tile {
         cfg.dynamicSmemBytes = TS::SMEM;
         cfg.stream = c->stream;
         cudaLaunchAttribute attr[1];
-        if (phases > 1) {
+        if (phases > 1 || any_seam) {
             attr[0].id = cudaLaunchAttributeCooperative;
             attr[0].val.cooperative = 1;
         } else {
@@ -210,25 +320,25 @@ struct Tile {
         }
         cfg.attrs = attr;
         cfg.numAttrs = 1;
-        const int a = c->cur, b = c->cur ^ 1;
-        hs::Geom g = c->geom();
-        g.oy0 = row0;                                          // rows this launch produces
-        g.oy1 = row1;
-        return cudaLaunchKernelEx(&cfg, kernel(), c->tm_u[a], c->tm_v[a], c->tm_u[b], c->tm_v[b], c->tm_cpk,
-                                  c->tm_inv, c->d_u[a], c->d_v[a], c->d_u[b], c->d_v[b], c->d_done, g,
-                                  tg, kf, (float)(c->alpha * c->alpha));
+        return cudaLaunchKernelEx(&cfg, kernel<MAXS>(), d);
     }
-    static size_t tiles_for(const hs_ctx* c, int k) {          // tiles of one phase (row 0 even)
-        const int vx = TS::SX - round_up(RL * k, 4) - round_up(RR * k, 4);
-        const int hyt = RL * k + ((c->oy0 + c->grow0 + RL * k) & 1);
-        const int vy = (TS::SY - hyt - RR * k) & ~1;
-        if (vx <= 0 || vy <= 0) return 0;
-        return (size_t)((c->W + vx - 1) / vx) * ((c->oy1 - c->oy0 + vy - 1) / vy) * c->B;
+    static cudaError_t launch(hs_ctx* c, int k, int sweeps, int row0, int row1, bool seams = false) {
+        return launch_n<1>(&c, 1, k, sweeps, row0, row1, seams);
+    }
+    static cudaError_t launch_group(hs_ctx* const* cs, int n, int k, int sweeps) {
+        if (n < 1 || n > EMU_MAXS) return cudaErrorInvalidValue;
+        return launch_n<EMU_MAXS>(cs, n, k, sweeps, cs[0]->oy0, cs[0]->oy1, true);
+    }
+    static size_t tiles_for(const hs_ctx* c, int k) {          // tiles of one phase
+        const int vx = vx_of(k);
+        const RowTiling t = tiling(k, c->oy1 - c->oy0, c->oy0 + c->grow0);
+        if (vx <= 0 || t.vy <= 0) return 0;
+        return (size_t)((c->W + vx - 1) / vx) * t.tiles_y * c->B;
     }
     static size_t max_tiles(const hs_ctx* c) {                 // upper bound over all k (k = 1 tiles are the largest)
         size_t best = 0;
         for (int k = 1; k <= max_k(); ++k) {
-            const int vx = TS::SX - round_up(RL * k, 4) - round_up(RR * k, 4), vy = (TS::SY - (RL + RR) * k - 1) & ~1;
+            const int vx = vx_of(k), vy = (TS::SY - (RL + RR) * k - 1) & ~1;
             if (vx <= 0 || vy <= 0) break;
             const size_t n = (size_t)((c->W + vx - 1) / vx) * ((c->oy1 - c->oy0 + vy - 1) / vy) * c->B;
             best = std::max(best, n);
@@ -291,12 +401,12 @@ int do_upload(hs_ctx* c, const uint8_t* prev, size_t ps, size_t pis, const uint8
 
 int do_prepare(hs_ctx* c) {
     if (!c->uploaded) return fail(c, HS_ERR_STATE, "hs_prepare before frames were uploaded");
-    const size_t fbytes = (size_t)c->plane * c->B * sizeof(float);
-    for (int i = 0; i < 2; ++i) {
-        HS_CUDA(c, cudaMemsetAsync(c->d_u[i], 0, fbytes, c->stream));   // hornSchunck.cpp:49-50
-        HS_CUDA(c, cudaMemsetAsync(c->d_v[i], 0, fbytes, c->stream));
-    }
+    // u = v = 0 (hornSchunck.cpp:49-50): both plane pairs and the seam inbox are one allocation, one memset.
+    // A linked row slab must not get here while a neighbour's previous hs_iterate is still running
+    // (it stores into this arena): the group code orders that with events, separate processes barrier.
+    HS_CUDA(c, cudaMemsetAsync(c->arena, 0, c->arena_bytes, c->stream));
     c->cur = 0;
+    c->phase_count = 0;
     dim3 block(32, 8);
     dim3 grid((c->pitch / 4 + 31) / 32, (c->H + 7) / 8, c->B);
     const float a2 = (float)(c->alpha * c->alpha);
@@ -322,9 +432,16 @@ int do_iterate(hs_ctx* c, int iters) {
         if (c->kernel_id == 1) {
             // everything in one multi-phase launch, unless the caller must refresh halos between
             // fused launches (row slabs) or asked for per-launch behaviour
-            step = c->multi_phase ? left : std::min(c->k, left);
-            tile_dispatch(c, [&](auto t) { e = decltype(t)::launch(c, std::min(c->k, step), step, c->oy0, c->oy1); });
-            if (e == cudaSuccess && (((step + c->k - 1) / c->k) & 1)) c->cur ^= 1;
+            // (a LINKED row slab exchanges its halos from inside the kernel: one launch as well)
+            step = (c->multi_phase || c->linked) ? left : std::min(c->k, left);
+            // (linked slabs keep the tile geometry of k even for a short call: seam flags are laid out by it)
+            const int kk = c->linked ? c->k : std::min(c->k, step);
+            tile_dispatch(c, [&](auto t) { e = decltype(t)::launch(c, kk, step, c->oy0, c->oy1, c->linked); });
+            const int phases = (step + kk - 1) / kk;
+            if (e == cudaSuccess) {
+                if (phases & 1) c->cur ^= 1;
+                c->phase_count += phases;
+            }
         } else {
             dim3 block(32, 8);
             dim3 grid((c->W + 31) / 32, (c->oy1 - c->oy0 + 7) / 8, c->B);
@@ -381,8 +498,11 @@ int do_download(hs_ctx* c, void* u, size_t us, size_t uis, void* v, size_t vs, s
     return HS_OK;
 }
 
+void group_destroy(hs_ctx* g);
+
 void destroy_impl(hs_ctx* c) {
     if (!c) return;
+    if (!c->kids.empty() || c->nccl) group_destroy(c);
     {
         DevGuard g(c->dev);
         if (c->stream) cudaStreamSynchronize(c->stream);
@@ -392,7 +512,9 @@ void destroy_impl(hs_ctx* c) {
         if (c->ev_up) cudaEventDestroy(c->ev_up);
         for (auto& e : c->ev_k1) if (e) cudaEventDestroy(e);
         for (auto& e : c->ev_solved) if (e) cudaEventDestroy(e);
-        for (int i = 0; i < 2; ++i) { cudaFree(c->d_u[i]); cudaFree(c->d_v[i]); }
+        if (c->ipc_up) cudaIpcCloseMemHandle(c->ipc_up);
+        if (c->ipc_dn) cudaIpcCloseMemHandle(c->ipc_dn);
+        cudaFree(c->arena);
         cudaFree(c->d_cpk); cudaFree(c->d_inv); cudaFree(c->d_done); cudaFree(c->d_bgr); cudaFree(c->d_resid); cudaFree(c->d_out);
         for (auto& e : c->ev) if (e) cudaEventDestroy(e);
         if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
@@ -400,6 +522,20 @@ void destroy_impl(hs_ctx* c) {
     delete c;
 }
 
+}  // namespace
+
+namespace {
+int group_upload(hs_ctx* g, const uint8_t* prev, size_t ps, size_t pis, const uint8_t* next, size_t ns, size_t nis);
+int group_prepare(hs_ctx* g);
+int group_iterate(hs_ctx* g, int iters);
+int group_download(hs_ctx* g, void* u, size_t us, size_t uis, void* v, size_t vs, size_t vis, int dt);
+int group_sync(hs_ctx* g);
+int group_solve_device(hs_ctx* g);
+int group_solve(hs_ctx* g, const uint8_t* prev, size_t ps, size_t pis, const uint8_t* next, size_t ns, size_t nis,
+                void* u, size_t us, size_t uis, void* v, size_t vs, size_t vis, int dt);
+int create_single(const hs_config& cfg, hs_ctx** out);
+int create_group(const hs_config& cfg, hs_ctx** out);
+int create_slab_rank(const hs_config& cfg, hs_ctx** out);
 }  // namespace
 
 extern "C" {
@@ -416,6 +552,17 @@ int hs_create(const hs_config* cfg_in, hs_ctx** out) {
                     cfg_in->struct_size, sizeof(hs_config));
     hs_config cfg{};
     memcpy(&cfg, cfg_in, cfg_in->struct_size);
+    if (cfg.num_devices > 1) return create_group(cfg, out);
+    if (cfg.slab_world > 1) return create_slab_rank(cfg, out);
+    return create_single(cfg, out);
+}
+
+}  // extern "C"
+
+namespace {
+
+int create_single(const hs_config& cfg_in, hs_ctx** out) {
+    hs_config cfg = cfg_in;
     if (cfg.width < 1 || cfg.height < 1) return fail(nullptr, HS_ERR_INVALID_ARG, "width and height must be >= 1");
     if (cfg.window_size < 1) return fail(nullptr, HS_ERR_INVALID_ARG, "window_size must be >= 1");
     if (cfg.max_iterations < 0) return fail(nullptr, HS_ERR_INVALID_ARG, "max_iterations must be >= 0");
@@ -491,9 +638,21 @@ int hs_create(const hs_config* cfg_in, hs_ctx** out) {
     const size_t npx = (size_t)c->plane * c->B;
     HS_CREATE_CUDA(cudaMalloc(&c->d_prev, c->fimg * c->B));
     HS_CREATE_CUDA(cudaMalloc(&c->d_next, c->fimg * c->B));
-    for (int i = 0; i < 2; ++i) {
-        HS_CREATE_CUDA(cudaMalloc(&c->d_u[i], npx * sizeof(float)));
-        HS_CREATE_CUDA(cudaMalloc(&c->d_v[i], npx * sizeof(float)));
+    {   // the four flow planes and the seam inbox share ONE allocation: a single memset zeroes the state
+        // (:49-50), and a single IPC handle exposes everything a neighbouring slab writes to
+        const size_t pbytes = (npx * sizeof(float) + 255) / 256 * 256;
+        const size_t ibytes = (size_t)2 * hs::SEAM_JMAX * (c->W / 32 + 2) * sizeof(int);
+        c->inbox_off = 4 * pbytes;
+        c->arena_bytes = c->inbox_off + (ibytes + 255) / 256 * 256;
+        HS_CREATE_CUDA(cudaMalloc(&c->arena, c->arena_bytes));
+        char* base = static_cast<char*>(c->arena);
+        for (int i = 0; i < 4; ++i) c->plane_off[i] = (size_t)i * pbytes;
+        c->d_u[0] = reinterpret_cast<float*>(base + c->plane_off[0]);
+        c->d_v[0] = reinterpret_cast<float*>(base + c->plane_off[1]);
+        c->d_u[1] = reinterpret_cast<float*>(base + c->plane_off[2]);
+        c->d_v[1] = reinterpret_cast<float*>(base + c->plane_off[3]);
+        c->d_inbox = reinterpret_cast<int*>(base + c->inbox_off);
+        c->max_ctas = env_int("HS_MAX_CTAS", 0);
     }
     HS_CREATE_CUDA(cudaMalloc(&c->d_cpk, npx * sizeof(uint32_t)));
     HS_CREATE_CUDA(cudaMalloc(&c->d_inv, npx * sizeof(float)));
@@ -607,30 +766,50 @@ int hs_create(const hs_config* cfg_in, hs_ctx** out) {
 #undef HS_CREATE_CUDA
 }
 
+}  // namespace
+
+#include "hs_multi.inl"
+
+extern "C" {
+
 void hs_destroy(hs_ctx* ctx) { destroy_impl(ctx); }
+
+#define HS_NO_GROUP(c, name)                                                                              \
+    if (!(c)->kids.empty())                                                                               \
+        return fail((c), HS_ERR_UNSUPPORTED, name " is not available on a multi-device context (use hs_solve, "   \
+                                             "or hs_upload / hs_solve_device / hs_download / hs_sync)")
 
 int hs_upload(hs_ctx* c, const uint8_t* prev, size_t ps, size_t pis, const uint8_t* next, size_t ns, size_t nis) {
     if (!c) return HS_ERR_INVALID_ARG;
+    if (!c->kids.empty()) return group_upload(c, prev, ps, pis, next, ns, nis);
     DevGuard g(c->dev);
     return do_upload(c, prev, ps, pis, next, ns, nis);
 }
 
 int hs_prepare(hs_ctx* c) {
     if (!c) return HS_ERR_INVALID_ARG;
+    if (!c->kids.empty()) return group_prepare(c);
     DevGuard g(c->dev);
     return do_prepare(c);
 }
 
 int hs_iterate(hs_ctx* c, int iterations) {
     if (!c) return HS_ERR_INVALID_ARG;
-    if ((c->top_seam || c->bot_seam) && iterations > c->k)
-        return fail(c, HS_ERR_UNSUPPORTED, "row-slab context: at most temporal_k=%d sweeps between halo refreshes", c->k);
+    if (!c->kids.empty()) {
+        if (!c->prepared) return fail(c, HS_ERR_STATE, "hs_iterate before hs_prepare");
+        return group_iterate(c, iterations);
+    }
+    if ((c->top_seam || c->bot_seam) && !c->linked && iterations > c->k)
+        return fail(c, HS_ERR_UNSUPPORTED, "row-slab context that is not linked to its neighbours (hs_slab_connect): at most "
+                                           "temporal_k=%d sweeps between halo refreshes", c->k);
     DevGuard g(c->dev);
     return do_iterate(c, iterations);
 }
 
 int hs_iterate_rows(hs_ctx* c, int sweeps, int row_begin, int row_end, int flip) {
     if (!c) return HS_ERR_INVALID_ARG;
+    HS_NO_GROUP(c, "hs_iterate_rows");
+    if (c->linked) return fail(c, HS_ERR_STATE, "hs_iterate_rows on a connected row slab: hs_iterate exchanges the halos itself");
     if (!c->prepared) return fail(c, HS_ERR_STATE, "hs_iterate_rows before hs_prepare");
     if (c->kernel_id != 1) return fail(c, HS_ERR_UNSUPPORTED, "hs_iterate_rows needs the fused kernel (window 2..5)");
     if (sweeps < 1 || sweeps > c->k) return fail(c, HS_ERR_INVALID_ARG, "sweeps must be in [1, temporal_k=%d]", c->k);
@@ -648,6 +827,7 @@ int hs_iterate_rows(hs_ctx* c, int sweeps, int row_begin, int row_end, int flip)
 
 int hs_iterate_until(hs_ctx* c, int max_sweeps, double tolerance, int check_every, int* sweeps_done, double* residual) {
     if (!c) return HS_ERR_INVALID_ARG;
+    HS_NO_GROUP(c, "hs_iterate_until");
     if (!c->prepared) return fail(c, HS_ERR_STATE, "hs_iterate_until before hs_prepare");
     if (max_sweeps < 0 || check_every < 1 || !(tolerance >= 0)) return fail(c, HS_ERR_INVALID_ARG, "bad early-exit arguments");
     if (c->top_seam || c->bot_seam) return fail(c, HS_ERR_UNSUPPORTED, "hs_iterate_until needs a whole-image context");
@@ -679,6 +859,7 @@ int hs_iterate_until(hs_ctx* c, int max_sweeps, double tolerance, int check_ever
 
 int hs_solve_device(hs_ctx* c) {
     if (!c) return HS_ERR_INVALID_ARG;
+    if (!c->kids.empty()) return group_solve_device(c);
     if (c->top_seam || c->bot_seam)
         return fail(c, HS_ERR_UNSUPPORTED, "hs_solve_device on a row-slab context: halos must be refreshed every "
                                            "temporal_k sweeps (use hs_iterate / hs_iterate_rows or hs_slab_*)");
@@ -696,6 +877,10 @@ int hs_solve_device(hs_ctx* c) {
 
 int hs_download(hs_ctx* c, void* u, size_t us, size_t uis, void* v, size_t vs, size_t vis, int dt) {
     if (!c) return HS_ERR_INVALID_ARG;
+    if (!c->kids.empty()) {
+        int rc = group_download(c, u, us, uis, v, vs, vis, dt);
+        return rc ? rc : group_sync(c);
+    }
     DevGuard g(c->dev);
     int rc = do_download(c, u, us, uis, v, vs, vis, dt);
     if (rc) return rc;
@@ -705,6 +890,7 @@ int hs_download(hs_ctx* c, void* u, size_t us, size_t uis, void* v, size_t vs, s
 
 int hs_sync(hs_ctx* c) {
     if (!c) return HS_ERR_INVALID_ARG;
+    if (!c->kids.empty()) return group_sync(c);
     DevGuard g(c->dev);
     HS_CUDA(c, cudaStreamSynchronize(c->stream));
     if (c->timing_pending) {
@@ -720,6 +906,7 @@ int hs_sync(hs_ctx* c) {
 int hs_solve(hs_ctx* c, const uint8_t* prev, size_t ps, size_t pis, const uint8_t* next, size_t ns, size_t nis,
              void* u, size_t us, size_t uis, void* v, size_t vs, size_t vis, int dt) {
     if (!c) return HS_ERR_INVALID_ARG;
+    if (!c->kids.empty()) return group_solve(c, prev, ps, pis, next, ns, nis, u, us, uis, v, vs, vis, dt);
     if (c->top_seam || c->bot_seam)
         return fail(c, HS_ERR_UNSUPPORTED, "hs_solve on a row-slab context: halos must be refreshed every temporal_k "
                                            "sweeps (use hs_iterate / hs_iterate_rows or hs_slab_*)");
@@ -747,6 +934,7 @@ int hs_solve(hs_ctx* c, const uint8_t* prev, size_t ps, size_t pis, const uint8_
 int hs_solve_bgr(hs_ctx* c, const uint8_t* prev, size_t ps, const uint8_t* next, size_t ns,
                  void* u, size_t us, void* v, size_t vs, int dt) {
     if (!c) return HS_ERR_INVALID_ARG;
+    HS_NO_GROUP(c, "hs_solve_bgr");
     if (c->B != 1 || c->top_seam || c->bot_seam)
         return fail(c, HS_ERR_UNSUPPORTED, "hs_solve_bgr needs a whole-image, batch == 1 context");
     if (!prev || !next) return fail(c, HS_ERR_INVALID_ARG, "null frame pointer");
@@ -788,6 +976,7 @@ int hs_solve_bgr(hs_ctx* c, const uint8_t* prev, size_t ps, const uint8_t* next,
 int hs_gradients(hs_ctx* c, const uint8_t* prev, size_t ps, const uint8_t* next, size_t ns, void* gx, void* gy,
                  void* gt, size_t os, int dt) {
     if (!c) return HS_ERR_INVALID_ARG;
+    HS_NO_GROUP(c, "hs_gradients");
     if (c->B != 1) return fail(c, HS_ERR_UNSUPPORTED, "hs_gradients needs a batch == 1 context");
     if (!gx || !gy || !gt) return fail(c, HS_ERR_INVALID_ARG, "null output pointer");
     if (dt != HS_F32 && dt != HS_F64) return fail(c, HS_ERR_INVALID_ARG, "bad out_dtype");
@@ -823,6 +1012,7 @@ int hs_gradients(hs_ctx* c, const uint8_t* prev, size_t ps, const uint8_t* next,
 
 int hs_sample_grid(hs_ctx* c, int delta, double* u, double* v, int* ny_out, int* nx_out) {
     if (!c || delta < 1) return HS_ERR_INVALID_ARG;
+    HS_NO_GROUP(c, "hs_sample_grid");
     if (c->B != 1) return fail(c, HS_ERR_UNSUPPORTED, "hs_sample_grid needs a batch == 1 context");
     const int rows = c->oy1 - c->oy0;
     const int ny = (rows + delta - 1) / delta, nx = (c->W + delta - 1) / delta;
@@ -845,6 +1035,7 @@ int hs_sample_grid(hs_ctx* c, int delta, double* u, double* v, int* ny_out, int*
 
 int hs_get_device_view(hs_ctx* c, hs_device_view* o) {
     if (!c || !o) return HS_ERR_INVALID_ARG;
+    HS_NO_GROUP(c, "hs_get_device_view");
     o->prev = c->d_prev; o->next = c->d_next;
     o->frame_pitch = c->fpitch; o->frame_pair_stride = c->fimg;
     o->frame_rows = c->frows; o->frame_row0 = c->frow0;
@@ -945,6 +1136,7 @@ extern "C" int hs_video_push(hs_ctx* c, const uint8_t* frame, size_t stride, voi
                              int dt, int* pair_index) {
     if (!c || !pair_index) return HS_ERR_INVALID_ARG;
     *pair_index = -1;
+    HS_NO_GROUP(c, "hs_video_push");
     if (!frame) return fail(c, HS_ERR_INVALID_ARG, "null frame pointer");
     if (stride < (size_t)c->W) return fail(c, HS_ERR_INVALID_ARG, "row stride smaller than width");
     DevGuard g(c->dev);

@@ -434,8 +434,8 @@ struct TileShape {
     static constexpr size_t BYTES_EX = 2 * 2 * EX_FIELD * 4;
     static_assert(BYTES_EX <= STAGE, "exchange array must fit in one stage");
     static constexpr size_t OFF_BAR = 2 * STAGE;
-    static constexpr size_t OFF_INFO = OFF_BAR + 64;                  // int4 x 2: decoded (x0, y0, pair, phase) of the staged items
-    static constexpr size_t SMEM = OFF_INFO + 32;                     // full[2], empty[2], stored[2]; item info
+    static constexpr size_t OFF_INFO = OFF_BAR + 64;                  // int4 x 2 x 2: decoded (x0, y0, pair, phase | slab, ...) of the staged items
+    static constexpr size_t SMEM = OFF_INFO + 64;                     // full[2], empty[2], stored[2]; item info
     static constexpr uint32_t TX_BYTES = (uint32_t)STAGE;
     // slot of patch row j in the exchange array (-1: no neighbour reads it)
     __host__ __device__ static constexpr int slot(int j) {
@@ -656,14 +656,77 @@ __device__ long long g_tile_prof[256][8];
 #define HS_PROF_ADD(slot, a, b)
 #endif
 
-// geometry of one launch (host-computed, same for every tile)
-struct TileGrid {
+// One row slab (or a whole image) of a launch: its planes, TMA maps, tile geometry and - for the
+// row-slab decomposition over several GPUs - its two seams.  Host-computed, passed by value.
+//
+// Seams.  A slab's buffer holds its own rows [oy0, oy1) plus halo rows above / below that belong to
+// the neighbouring slabs (other GPUs).  Nothing is exchanged between launches: a tile that finishes
+// a phase stores the rows the neighbour's next phase will read STRAIGHT INTO THE NEIGHBOUR'S HALO
+// ROWS (peer memory over NVLink, plain vector stores), and its producer warp then publishes the
+// tile's phase count in the neighbour's `inbox` (fence.acq_rel.sys + st.release.sys).  The
+// neighbour's producer warp polls its own inbox (local memory) next to the local `done[]` counters
+// before it issues the TMA loads of a seam tile.  The rule is the one used inside a GPU - a tile
+// may start phase p once every tile whose rows it reads, or that reads the rows it will overwrite,
+// has finished phase p-1 - so the read-after-write on the halo rows and the write-after-read on the
+// ping-pong plane are both covered.  Flags are ABSOLUTE phase counts since hs_prepare (`phase_base`
+// + phase of the launch + 1), so they never have to be reset while neighbours are running.
+constexpr int SEAM_JMAX = 2;   // tile rows of a slab that can touch one seam (halos fit in one tile pitch)
+
+// n / d for 0 <= n < 2^31 as one multiply-high and a shift (host computes mul, shr).  The producer
+// warp decodes one work item per tile on a latency chain of its own; real divisions there cost more
+// than the TMA issue they precede.
+struct FastDiv {
+    uint32_t mul, shr, d;
+    __host__ __device__ static FastDiv make(uint32_t den) {
+        FastDiv f; f.d = den; f.mul = 0; f.shr = 0;
+        if (den > 1) {
+            uint32_t lg = 0;
+            while ((1ull << lg) < den) ++lg;
+            const uint32_t pw = 31 + lg;
+            f.mul = (uint32_t)(((1ull << pw) + den - 1) / den);
+            f.shr = pw - 32;
+        }
+        return f;
+    }
+    __device__ __forceinline__ int div(int n) const { return d == 1 ? n : (int)(__umulhi((uint32_t)n, mul) >> shr); }
+};
+struct SlabDesc {
+    CUtensorMap tm_u[2], tm_v[2], tm_cpk, tm_inv;
+    float* u[2];
+    float* v[2];
+    Geom g;                    // oy0 / oy1 = the rows this launch produces
+    int hyt, vy;               // halo rows above the stored centre of a tile; rows of the centre
+    int tiles_y, ntiles;       // tile rows; tiles_x * tiles_y * batch
+    int tile0;                 // index of the slab's first tile in done[] and in the item stream
+    FastDiv fd_per_img;        // / (tiles_x * tiles_y)
+    int reverse;               // walk the tile rows bottom-up (odd slabs: both sides of a seam are then
+                               //   processed at the same end of a phase, a whole phase before they are needed)
+    // --- seams; null pointers = no neighbour on that side -----------------------------------
+    float* up_u[2]; float* up_v[2];   // the planes of the slab above / below (peer memory)
+    float* dn_u[2]; float* dn_v[2];
+    int up_dy, dn_dy;          // buffer row y of this slab is buffer row y + dy of that neighbour
+    int push_up, push_dn;      // the first push_up / last push_dn produced rows are halo rows of the neighbour
+    int* inbox;                // [2][SEAM_JMAX][tiles_x]: phase counts published by the slab above ([0]) / below ([1])
+    int* out_up; int* out_dn;  // where this slab publishes: the neighbours' inbox blocks for this side
+    int jt, jb;                // tile rows [0, jt) touch the seam above, [tiles_y - jb, tiles_y) the seam below
+    int up_j, dn_j;            // flag rows to wait for in inbox[0] / inbox[1] (the neighbour's jb / jt); 0 = no seam
+};
+
+// geometry of one launch (host-computed)
+template <int MAXS>
+struct LaunchDesc {
+    SlabDesc s[MAXS];
+    int nslabs;
     int k;                 // sweeps fused per phase (tile geometry is sized for this)
     int sweeps;            // total sweeps of this launch = phases * k (the last phase may be short)
-    int hxl, hyt;          // halo columns left / rows above the stored centre
-    int vx, vy;            // stored centre of a tile
-    int tiles_x, tiles_y;  // tiles per image
-    int ntiles;            // tiles_x * tiles_y * batch
+    int cur;               // phase p reads planes [cur ^ (p & 1)] and writes the other pair
+    int phase_base;        // phases completed since hs_prepare (seam flags are absolute)
+    int hxl, vx;           // halo columns left of / columns of the stored centre of a tile
+    int tiles_x;           // tile columns (all slabs have the same width)
+    FastDiv fd_tiles_x;
+    int ntiles;            // all tiles of all slabs
+    int* done;             // per-tile phase counters of this launch (zeroed by the host)
+    float kf, alpha2;
 };
 
 // gpu-scope flag helpers for the inter-CTA dataflow of a multi-phase launch
@@ -676,7 +739,37 @@ __device__ __forceinline__ void st_release_gpu(int* p, int v) {
     asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 __device__ __forceinline__ void fence_acq_rel_gpu() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
-__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+// system scope: flags and halo rows that cross NVLink (row-slab seams)
+__device__ __forceinline__ int ld_relaxed_sys(const int* p) {
+    int v;
+    asm volatile("ld.relaxed.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys(int* p, int v) {
+    asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void fence_acq_rel_sys() { asm volatile("fence.acq_rel.sys;" ::: "memory"); }
+// generic <-> async proxy ordering for GLOBAL memory only: FENCE.VIEW.ASYNC.G, no MEMBAR (the
+// unqualified fence.proxy.async also emits a MEMBAR.ALL.GPU, ~1.5k cycles on the producer's chain)
+__device__ __forceinline__ void fence_proxy_async_global() { asm volatile("fence.proxy.async.global;" ::: "memory"); }
+// acquire loads: LDG.STRONG + CCTL.IVALL, again no MEMBAR (a relaxed load + fence.acq_rel would wait
+// for every outstanding store of the SM, which an acquire has no use for)
+__device__ __forceinline__ int ld_acquire_gpu(const int* p) {
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ int ld_acquire_sys(const int* p) {
+    int v;
+    asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_relaxed_gpu(int* p, int v) {
+    asm volatile("st.relaxed.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void st_relaxed_sys(int* p, int v) {
+    asm volatile("st.relaxed.sys.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
 
 // One launch = `phases` phases of up to k sweeps over every tile.  Phase p reads the flow planes
 // (p & 1) and writes the planes ((p & 1) ^ 1).  There is NO grid-wide barrier between phases:
@@ -693,13 +786,14 @@ __device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.pr
 // TMA boxes of the next item into the free stage (empty[] -> full[] mbarriers) and publishes this
 // CTA's finished tiles (stored[] mbarrier -> fence -> counter), polling all of that without ever
 // blocking on one duty, so a CTA can never hold back a tile somebody else is waiting for.
-template <int RL, int RR, int R, int NWARP, bool TB = false>
+//
+// MAXS = 1 is the production instantiation (one slab or whole image per launch and GPU).  MAXS > 1
+// runs several row slabs of ONE device in one cooperative launch: the seam protocol (peer stores,
+// system-scope flags) is then exercised end to end on a single GPU, without kernels of different
+// launches waiting on each other.
+template <int RL, int RR, int R, int NWARP, bool TB = false, int MAXS = 1>
 __global__ void __launch_bounds__(NWARP * 32 + 128, 1)
-k_jacobi_tile(const __grid_constant__ CUtensorMap tm_u0, const __grid_constant__ CUtensorMap tm_v0,
-              const __grid_constant__ CUtensorMap tm_u1, const __grid_constant__ CUtensorMap tm_v1,
-              const __grid_constant__ CUtensorMap tm_cpk, const __grid_constant__ CUtensorMap tm_inv,
-              float* __restrict__ u0, float* __restrict__ v0, float* __restrict__ u1, float* __restrict__ v1,
-              int* __restrict__ done, Geom g, TileGrid tg, float kf, float alpha2) {
+k_jacobi_tile(const __grid_constant__ LaunchDesc<MAXS> d) {
     using TS = TileShape<RL, RR, R, NWARP>;
     static_assert(!TB || (RL == 1 && RR == 1), "the textbook average is a 3x3 stencil");
     static_assert(R * 4 <= 32, "in-image mask is one 32-bit word per thread");
@@ -713,28 +807,45 @@ k_jacobi_tile(const __grid_constant__ CUtensorMap tm_u0, const __grid_constant__
     const int tid = threadIdx.x;
     const int lane = tid & 31;
     const int warp = tid >> 5;
-    const int per_img = tg.tiles_x * tg.tiles_y;
     const int G = gridDim.x;
-    const int phases = (tg.sweeps + tg.k - 1) / tg.k;
-    const int total = phases * tg.ntiles;             // work items of the launch, phase-major: g = p*ntiles + t
+    const int phases = (d.sweeps + d.k - 1) / d.k;
+    const int total = phases * d.ntiles;              // work items of the launch, phase-major: g = p*ntiles + t
     const int items = (total - (int)blockIdx.x + G - 1) / G;   // ... of this CTA (>= 1: grid <= ntiles)
+    int* __restrict__ done = d.done;
 
     // CTA c takes items c, c+G, c+2G, ... of the global phase-major stream.  Unless G divides the
     // tile count this rotates the tile -> CTA assignment from phase to phase, so the slower border
     // tiles (masked path) are shared by everybody instead of pinning a few CTAs that all their
     // neighbours then have to wait for.
-    struct Item { int p, t, b, bx, by, x0, y0; };
-    auto item_of = [&](int n) {
-        const int gi = blockIdx.x + n * G;
+    // t: index in done[] (all slabs); by: the REAL tile row; pub_up / pub_dn: where a seam tile publishes
+    // in the neighbour's inbox (-1: not a seam tile)
+    struct Item { int p, t, s, b, bx, by, x0, y0, pub_up, pub_dn; };
+    int seq_p = 0, seq_t = (int)blockIdx.x;           // the stream is walked in order: no division by ntiles
+    auto next_item = [&]() {
         Item it;
-        it.p = gi / tg.ntiles;
-        it.t = gi - it.p * tg.ntiles;
-        it.b = it.t / per_img;
-        const int r = it.t - it.b * per_img;
-        it.by = r / tg.tiles_x;
-        it.bx = r - it.by * tg.tiles_x;
-        it.x0 = it.bx * tg.vx - tg.hxl;               // staged tile origin (may be negative)
-        it.y0 = g.oy0 + it.by * tg.vy - tg.hyt;
+        it.p = seq_p;
+        const int t = seq_t;
+        seq_t += G;
+        if (seq_t >= d.ntiles) { seq_t -= d.ntiles; ++seq_p; }   // G <= ntiles: at most one wrap
+        it.s = 0;
+        if (MAXS > 1) {
+#pragma unroll
+            for (int q = 1; q < MAXS; ++q)
+                if (q < d.nslabs && t >= d.s[q].tile0) it.s = q;
+        }
+        const SlabDesc& S = d.s[it.s];
+        const int per_img = d.tiles_x * S.tiles_y;
+        const int lt = t - S.tile0;
+        it.b = S.fd_per_img.div(lt);
+        const int r = lt - it.b * per_img;
+        const int row = d.fd_tiles_x.div(r);          // position in this slab's walking order
+        it.bx = r - row * d.tiles_x;
+        it.by = S.reverse ? S.tiles_y - 1 - row : row;
+        it.t = S.tile0 + it.b * per_img + it.by * d.tiles_x + it.bx;
+        it.x0 = it.bx * d.vx - d.hxl;                 // staged tile origin (may be negative)
+        it.y0 = S.g.oy0 + it.by * S.vy - S.hyt;
+        it.pub_up = (S.out_up && it.by < S.jt) ? it.by * d.tiles_x + it.bx : -1;
+        it.pub_dn = (S.out_dn && it.by >= S.tiles_y - S.jb) ? (it.by - (S.tiles_y - S.jb)) * d.tiles_x + it.bx : -1;
         return it;
     };
 
@@ -752,37 +863,93 @@ k_jacobi_tile(const __grid_constant__ CUtensorMap tm_u0, const __grid_constant__
     // 512 threads are launched with 128 registers each (the whole register file).  The producer warp
     // group hands most of its share back and the three compute warp groups take it.
     if (warp >= NWARP) {
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
         if (warp > NWARP) return;
         // ================================ producer warp ================================
         // Start coordinates are multiples of 4 floats = 16 B: UTMALDG faults ("illegal instruction")
         // on sm_100a when the innermost start offset is not 16-byte aligned (tools/tma_probe.cu).
-        auto issue = [&](const Item& it, int stage, bool coef, bool flow) {   // lane 0 only
+        auto issue = [&](const Item& it, int stage) {   // lane 0 only
             unsigned char* st = smem + (size_t)stage * TS::STAGE;
-            if (coef) {   // coefficient boxes are never written by a sweep launch
-                // the decoded item travels with its boxes: the compute warps read it after the full[]
-                // wait instead of each redoing the divisions (the arrive below releases this store)
-                reinterpret_cast<int4*>(smem + TS::OFF_INFO)[stage] = make_int4(it.x0, it.y0, it.b, it.p);
-                mbar_expect_tx(&full[stage], TS::TX_BYTES);
-                tma_load_3d(st + TS::OFF_CPK, &tm_cpk, &full[stage], it.x0, it.y0, it.b);
-                tma_load_3d(st + TS::OFF_INV, &tm_inv, &full[stage], it.x0, it.y0, it.b);
-            }
-            if (flow) {
-                tma_load_3d(st + TS::OFF_U, (it.p & 1) ? &tm_u1 : &tm_u0, &full[stage], it.x0, it.y0, it.b);
-                tma_load_3d(st + TS::OFF_V, (it.p & 1) ? &tm_v1 : &tm_v0, &full[stage], it.x0, it.y0, it.b);
-            }
+            const SlabDesc& S = d.s[it.s];
+            const int rd = (d.cur ^ it.p) & 1;            // planes this phase reads
+            // the decoded item travels with its boxes: the compute warps read it after the full[]
+            // wait instead of each redoing the divisions (the arrive below releases this store)
+            int4* info = reinterpret_cast<int4*>(smem + TS::OFF_INFO) + 2 * stage;
+            info[0] = make_int4(it.x0, it.y0, it.b, it.p);
+            if (MAXS > 1) info[1] = make_int4(it.s, 0, 0, 0);
+            mbar_expect_tx(&full[stage], TS::TX_BYTES);
+            tma_load_3d(st + TS::OFF_CPK, &S.tm_cpk, &full[stage], it.x0, it.y0, it.b);
+            tma_load_3d(st + TS::OFF_INV, &S.tm_inv, &full[stage], it.x0, it.y0, it.b);
+            tma_load_3d(st + TS::OFF_U, &S.tm_u[rd], &full[stage], it.x0, it.y0, it.b);
+            tma_load_3d(st + TS::OFF_V, &S.tm_v[rd], &full[stage], it.x0, it.y0, it.b);
         };
         if (lane == 0) {
-            tma_prefetch_desc(&tm_u0);
-            tma_prefetch_desc(&tm_v0);
-            tma_prefetch_desc(&tm_u1);
-            tma_prefetch_desc(&tm_v1);
-            tma_prefetch_desc(&tm_cpk);
-            tma_prefetch_desc(&tm_inv);
+#pragma unroll
+            for (int q = 0; q < MAXS; ++q)
+                if (q < d.nslabs) {
+                    tma_prefetch_desc(&d.s[q].tm_u[0]);
+                    tma_prefetch_desc(&d.s[q].tm_v[0]);
+                    tma_prefetch_desc(&d.s[q].tm_u[1]);
+                    tma_prefetch_desc(&d.s[q].tm_v[1]);
+                    tma_prefetch_desc(&d.s[q].tm_cpk);
+                    tma_prefetch_desc(&d.s[q].tm_inv);
+                }
         }
         pdl_launch_dependents();      // the next launch may queue up behind us (it waits in pdl_wait)
         pdl_wait();                   // whatever wrote the planes we read (K1, a sweep launch, a halo copy) is done
-        if (lane == 0) issue(item_of(0), 0, true, true);
+        // A seam tile depends on the neighbouring slab (another GPU) even in the first phase of a launch:
+        // that slab's previous launch must have delivered its last phase.  Which tiles are seam tiles:
+        auto seam_sides = [&](const Item& it, bool& up, bool& dn) {
+            const SlabDesc& S = d.s[it.s];
+            up = S.up_j > 0 && it.by < S.jt;
+            dn = S.dn_j > 0 && it.by >= S.tiles_y - S.jb;
+        };
+        // Wait until everything item `nx` reads (or will overwrite) is finished: the 3 x 3 tiles around it
+        // in its own slab (done[], phases of this launch) and, for a seam tile, the facing tiles of the
+        // neighbouring slab (inbox, absolute phase counts).  `on_spin` runs while waiting.
+        auto wait_deps = [&](const Item& nx, auto&& on_spin) {
+            bool up, dn;
+            seam_sides(nx, up, dn);
+            const bool seam = (up || dn) && (d.phase_base + nx.p > 0);
+            if (nx.p == 0 && !seam) return;
+            const SlabDesc& S = d.s[nx.s];
+            const int per_img = d.tiles_x * S.tiles_y;
+            unsigned long long t0 = 0;
+            for (uint32_t spins = 0;; ++spins) {
+                int dep = 0x7fffffff;                 // lanes 0..8: one neighbour counter each
+                if (lane < 9) {
+                    const int yy = nx.by + lane / 3 - 1, xx = nx.bx + lane % 3 - 1;
+                    if (nx.p > 0 && yy >= 0 && yy < S.tiles_y && xx >= 0 && xx < d.tiles_x)
+                        dep = ld_acquire_gpu(done + S.tile0 + nx.b * per_img + yy * d.tiles_x + xx);
+                } else if (seam && lane < 9 + 6 * SEAM_JMAX) {   // lanes 9..: the neighbours' flags for 3 tile columns
+                    const int q = lane - 9;
+                    const int side = q / (3 * SEAM_JMAX), j = (q / 3) % SEAM_JMAX, xx = nx.bx + q % 3 - 1;
+                    const bool want = side == 0 ? (up && j < S.up_j) : (dn && j < S.dn_j);
+                    if (want && xx >= 0 && xx < d.tiles_x)
+                        dep = ld_acquire_sys(S.inbox + (side * SEAM_JMAX + j) * d.tiles_x + xx) - d.phase_base;
+                }
+                if (__reduce_min_sync(0xffffffffu, dep) >= nx.p) break;   // phase p-1 is complete around us
+                on_spin();
+                // no sleep: the counter loads take an L2 round trip each, that is pause enough, and
+                // a tile with little slack (ntiles / #CTAs is < 3 rounds at 1080p) should be
+                // picked up the moment its last neighbour is published
+                if ((spins & 0xff) == 0xff) {
+                    const unsigned long long now = global_ns();
+                    if (t0 == 0) t0 = now;
+                    else if (now - t0 > WAIT_LIMIT_NS) __trap();
+                }
+            }
+            // Every lane that observed a counter did so with an ACQUIRE load; a warp barrier carries the
+            // ordering over to lane 0, whose proxy fence extends it to the async-proxy (TMA) reads
+            // issued below (the publisher has the matching proxy fence before its release).
+            __syncwarp();
+            if (lane == 0) fence_proxy_async_global();
+        };
+        // the last three decoded items: publishing lags issuing by at most two
+        Item it_a, it_b, it_c = next_item();              // items mi-2, mi-1, mi
+        it_a = it_b = it_c;
+        wait_deps(it_c, [] {});
+        if (lane == 0) issue(it_c, 0);
 
         // The events the producer reacts to alternate strictly in time: "item m-2 stored" -> publish
         // it;  "stage free" (the compute warps passed the barrier of item m-1) -> issue item m.
@@ -791,19 +958,44 @@ k_jacobi_tile(const __grid_constant__ CUtensorMap tm_u0, const __grid_constant__
         // counters; it keeps publishing meanwhile, so this CTA never sits on a finished tile that
         // somebody else is waiting for (no cycle in the wait graph: dependencies always point to
         // items that are earlier in every CTA's order).
-        const bool publish = phases > 1;
+        bool any_seam = false;
+#pragma unroll
+        for (int q = 0; q < MAXS; ++q)
+            if (q < d.nslabs && (d.s[q].out_up || d.s[q].out_dn)) any_seam = true;
+        const bool publish = phases > 1 || any_seam;
         int np = 0;                   // next item to publish
+        int cur_mi = 0;               // index of the item held in it_c
         auto do_publish = [&](int n) {
             // all compute warps have stored item n (their arrive is ordered after their stores);
             // make those stores visible GPU-wide, then bump the tile's counter
             if (lane == 0) {
-                const Item it = item_of(n);
-                fence_acq_rel_gpu();
-                st_release_gpu(done + it.t, it.p + 1);
+                const int age = cur_mi - n;               // 0, 1 or 2 (selected field by field: stays in registers)
+#define HS_PICK(f) (age == 0 ? it_c.f : (age == 1 ? it_b.f : it_a.f))
+                const int t = HS_PICK(t), p = HS_PICK(p), si = HS_PICK(s), pu = HS_PICK(pub_up), pd = HS_PICK(pub_dn);
+#undef HS_PICK
+                const bool seam = (pu & pd) != -1;
+                // the tile's rows were written through the generic proxy and will be read by TMA (async
+                // proxy) on other SMs / GPUs: proxy fence, then ONE release (a MEMBAR that also covers the
+                // compute warps' stores: they happen-before this thread through the stored[] mbarrier)
+                fence_proxy_async_global();
+                if (!seam) {
+                    st_release_gpu(done + t, p + 1);
+                } else {
+                    // seam tiles: the halo rows are in the neighbour's memory once the system-scope fence
+                    // completes; then tell the local and the neighbour's producer warps
+                    fence_acq_rel_sys();
+                    st_relaxed_gpu(done + t, p + 1);
+                    const SlabDesc& S = d.s[MAXS > 1 ? si : 0];
+                    if (pu >= 0) st_relaxed_sys(S.out_up + pu, d.phase_base + p + 1);
+                    if (pd >= 0) st_relaxed_sys(S.out_dn + pd, d.phase_base + p + 1);
+                }
             }
         };
         for (int mi = 1; mi < items; ++mi) {
-            const Item nx = item_of(mi);
+            // items <= mi-3 are published (step (2) of the previous round), so slot a can be recycled
+            it_a = it_b; it_b = it_c; it_c = next_item();
+            cur_mi = mi;
+            const Item& nx = it_c;
             // (1) Dependencies first, while the compute warps are still busy with item mi-2/mi-1:
             // they are normally satisfied a whole phase ahead, and the L2 round trips of the
             // counter loads and of the two fences (~1.5k cycles each under load) stay off the
@@ -811,36 +1003,12 @@ k_jacobi_tile(const __grid_constant__ CUtensorMap tm_u0, const __grid_constant__
 #ifdef HS_TILE_PROFILE
             const long long prof_t0 = clock64();
 #endif
-            if (nx.p > 0) {
-                unsigned long long t0 = 0;
-                for (uint32_t spins = 0;; ++spins) {
-                    int dep = 0x7fffffff;             // lanes 0..8: one neighbour counter each
-                    if (lane < 9) {
-                        const int yy = nx.by + lane / 3 - 1, xx = nx.bx + lane % 3 - 1;
-                        if (yy >= 0 && yy < tg.tiles_y && xx >= 0 && xx < tg.tiles_x)
-                            dep = ld_relaxed_gpu(done + nx.b * per_img + yy * tg.tiles_x + xx);
-                    }
-                    if (__reduce_min_sync(0xffffffffu, dep) >= nx.p) break;   // phase p-1 is complete around us
-                    if (np < mi && mbar_test(&stored[np & 1], (np >> 1) & 1)) {
-                        do_publish(np);
-                        ++np;
-                    }
-                    // no sleep: the counter loads take an L2 round trip each, that is pause enough, and
-                    // a tile with little slack (ntiles / #CTAs is < 3 rounds at 1080p) should be
-                    // picked up the moment its last neighbour is published
-                    if ((spins & 0xff) == 0xff) {
-                        const unsigned long long now = global_ns();
-                        if (t0 == 0) t0 = now;
-                        else if (now - t0 > WAIT_LIMIT_NS) __trap();
-                    }
+            wait_deps(nx, [&] {
+                if (publish && np < mi && mbar_test(&stored[np & 1], (np >> 1) & 1)) {
+                    do_publish(np);
+                    ++np;
                 }
-                // Acquire on EVERY lane that observed a counter (relaxed load + fence is the acquire
-                // pattern of the thread that loaded), then a warp barrier carries the ordering over
-                // to lane 0, whose proxy fence extends it to the async-proxy (TMA) reads issued below.
-                fence_acq_rel_gpu();
-                __syncwarp();
-                if (lane == 0) fence_proxy_async_all();
-            }
+            });
 #ifdef HS_TILE_PROFILE
             const long long prof_t1 = clock64();
 #endif
@@ -853,7 +1021,7 @@ k_jacobi_tile(const __grid_constant__ CUtensorMap tm_u0, const __grid_constant__
             // (3) the stage of item mi is free once the compute warps passed the barrier of item mi-1
             if (mi >= 2) mbar_wait(&empty[mi & 1], ((mi - 2) >> 1) & 1);
             if (lane == 0) {
-                issue(nx, mi & 1, true, true);
+                issue(nx, mi & 1);
 #ifdef HS_TILE_PROFILE
                 if (mi >= 2) {
                     g_tile_prof[blockIdx.x][7] += clock64() - reinterpret_cast<volatile long long*>(smem + TS::OFF_BAR + 48)[0];
@@ -886,8 +1054,11 @@ k_jacobi_tile(const __grid_constant__ CUtensorMap tm_u0, const __grid_constant__
         mbar_wait(&full[stage], (n >> 1) & 1);
         HS_PROF_T(pt1);
 
-        const int4 info = reinterpret_cast<const int4*>(smem + TS::OFF_INFO)[stage];   // decoded by the producer
+        const int4 info = reinterpret_cast<const int4*>(smem + TS::OFF_INFO)[2 * stage];   // decoded by the producer
         const int tx0 = info.x, ty0 = info.y, b = info.z, cur_p = info.w;
+        const int si = MAXS > 1 ? reinterpret_cast<const int4*>(smem + TS::OFF_INFO)[2 * stage + 1].x : 0;
+        const SlabDesc& S = d.s[si];
+        const Geom& g = S.g;
         const int gx0 = tx0 + lane * 4;
         const int gy0 = ty0 + row0;
         const bool tile_inside = (tx0 >= 0) && (tx0 + TS::SX <= g.W) && (ty0 >= 0) && (ty0 + TS::SY <= g.H);
@@ -921,7 +1092,7 @@ k_jacobi_tile(const __grid_constant__ CUtensorMap tm_u0, const __grid_constant__
                 unpack_coef_tb(qc.z, ix[j][2], iy[j][2]);
                 unpack_coef_tb(qc.w, ix[j][3], iy[j][3]);
 #pragma unroll
-                for (int c = 0; c < 4; ++c) iv[j][c] = hs_inv(ix[j][c], iy[j][c], alpha2);
+                for (int c = 0; c < 4; ++c) iv[j][c] = hs_inv(ix[j][c], iy[j][c], d.alpha2);
             } else {
                 iv[j][0] = qi.x; iv[j][1] = qi.y; iv[j][2] = qi.z; iv[j][3] = qi.w;
                 unpack_coef(qc.x, ix[j][0], iy[j][0], it[j][0]);
@@ -941,30 +1112,47 @@ k_jacobi_tile(const __grid_constant__ CUtensorMap tm_u0, const __grid_constant__
         HS_PROF_T(pt2);
 
         float* s_ex = reinterpret_cast<float*>(st);
-        const int kk = min(tg.k, tg.sweeps - cur_p * tg.k);
+        const int kk = min(d.k, d.sweeps - cur_p * d.k);
         if (tile_inside)
-            tile_sweeps<RL, RR, R, NWARP, false, TB>(u, v, ix, iy, it, iv, s_ex, kk, kf, warp, lane, inmask);
+            tile_sweeps<RL, RR, R, NWARP, false, TB>(u, v, ix, iy, it, iv, s_ex, kk, d.kf, warp, lane, inmask);
         else
-            tile_sweeps<RL, RR, R, NWARP, true, TB>(u, v, ix, iy, it, iv, s_ex, kk, kf, warp, lane, inmask);
+            tile_sweeps<RL, RR, R, NWARP, true, TB>(u, v, ix, iy, it, iv, s_ex, kk, d.kf, warp, lane, inmask);
 
         HS_PROF_T(pt3);
         // store the exact centre of the tile into the other pair of planes
         const int lx = lane * 4;
-        if (lx >= tg.hxl && lx < tg.hxl + tg.vx && gx0 < g.W) {
-            float* U = ((cur_p & 1) ? u0 : u1) + (size_t)b * g.plane;
-            float* V = ((cur_p & 1) ? v0 : v1) + (size_t)b * g.plane;
+        if (lx >= d.hxl && lx < d.hxl + d.vx && gx0 < g.W) {
+            const int wr = (d.cur ^ cur_p ^ 1) & 1;       // planes this phase writes
+            float* U = S.u[wr] + (size_t)b * g.plane;
+            float* V = S.v[wr] + (size_t)b * g.plane;
+            // row-slab seams: rows that are halo rows of a neighbouring slab also go straight into that
+            // slab's planes (peer memory over NVLink; all slabs flip their planes in lock step)
+            float* const UU = S.up_u[wr]; float* const VU = S.up_v[wr];
+            float* const UD = S.dn_u[wr]; float* const VD = S.dn_v[wr];
 #pragma unroll
             for (int j = 0; j < R; ++j) {
                 const int ly = row0 + j;
                 const int gy = gy0 + j;
-                if (ly >= tg.hyt && ly < tg.hyt + tg.vy && gy < g.oy1) {
+                if (ly >= S.hyt && ly < S.hyt + S.vy && gy < g.oy1) {
                     const size_t o = (size_t)gy * g.pitch + gx0;
-                    *reinterpret_cast<float4*>(U + o) = make_float4(u[j][0], u[j][1], u[j][2], u[j][3]);
-                    *reinterpret_cast<float4*>(V + o) = make_float4(v[j][0], v[j][1], v[j][2], v[j][3]);
+                    const float4 qu = make_float4(u[j][0], u[j][1], u[j][2], u[j][3]);
+                    const float4 qv = make_float4(v[j][0], v[j][1], v[j][2], v[j][3]);
+                    *reinterpret_cast<float4*>(U + o) = qu;
+                    *reinterpret_cast<float4*>(V + o) = qv;
+                    if (UU && gy < g.oy0 + S.push_up) {
+                        const size_t oo = (size_t)(gy + S.up_dy) * g.pitch + gx0;
+                        *reinterpret_cast<float4*>(UU + oo) = qu;
+                        *reinterpret_cast<float4*>(VU + oo) = qv;
+                    }
+                    if (UD && gy >= g.oy1 - S.push_dn) {
+                        const size_t oo = (size_t)(gy + S.dn_dy) * g.pitch + gx0;
+                        *reinterpret_cast<float4*>(UD + oo) = qu;
+                        *reinterpret_cast<float4*>(VD + oo) = qv;
+                    }
                 }
             }
         }
-        if (phases > 1) {             // tell the producer this warp's share of the tile is stored
+        if (phases > 1 || S.out_up || S.out_dn) {   // tell the producer this warp's share of the tile is stored
             __syncwarp();
             if (lane == 0) mbar_arrive(&stored[stage]);
         }

@@ -35,7 +35,11 @@ class Solver:
     """One hs_ctx: fixed geometry and parameters, reusable across frame pairs."""
 
     def __init__(self, width, height, window_size, max_iterations, alpha, batch=1, device=-1,
-                 temporal_k=0, flags=0, out_rows=None, stream=None, global_row0=0):
+                 temporal_k=0, flags=0, out_rows=None, stream=None, global_row0=0,
+                 devices=None, decomposition=H.DECOMP_BATCH, exchange=H.EXCHANGE_PEER, slab=None):
+        """devices: list of CUDA ordinals -> ONE context over several GPUs (hs_config.num_devices),
+        `decomposition` H.DECOMP_BATCH or H.DECOMP_ROW_SLAB.  slab=(rank, world): this process holds
+        one row slab of a `height`-row image (one process per GPU); see slab_info / slab_connect."""
         self._lib = H.load_library()
         cfg = H.HsConfig()
         cfg.struct_size = C.sizeof(H.HsConfig)
@@ -47,6 +51,12 @@ class Solver:
             cfg.out_row_begin, cfg.out_row_end = int(out_rows[0]), int(out_rows[1])
         cfg.stream = stream
         cfg.global_row0 = int(global_row0)
+        if devices is not None and len(devices) > 1:
+            self._device_ids = (C.c_int32 * len(devices))(*[int(d) for d in devices])
+            cfg.num_devices, cfg.device_ids = len(devices), self._device_ids
+            cfg.decomposition, cfg.exchange = int(decomposition), int(exchange)
+        if slab is not None:
+            cfg.slab_rank, cfg.slab_world = int(slab[0]), int(slab[1])
         self._ctx = C.c_void_p()
         rc = self._lib.hs_create(C.byref(cfg), C.byref(self._ctx))
         if rc != H.HS_OK:
@@ -57,6 +67,31 @@ class Solver:
         self.flags = cfg.flags
         self.frame_rows = cfg.height + (1 if cfg.flags & H.FLAG_TOP_IS_SEAM else 0) + \
             (1 if cfg.flags & H.FLAG_BOTTOM_IS_SEAM else 0)
+        if slab is not None and cfg.slab_world > 1:      # this process holds one band of the image
+            info = self.slab_info()
+            self.frame_rows = info.frame_end - info.frame_begin
+            self.out_rows = (0, info.own_end - info.own_begin)   # download() returns exactly the owned rows
+
+    # -- row slabs across processes ------------------------------------------------------------
+    def slab_info(self) -> H.HsSlabInfo:
+        info = H.HsSlabInfo()
+        self._check(self._lib.hs_get_slab_info(self._ctx, C.byref(info)))
+        return info
+
+    def slab_export(self) -> bytes:
+        """256 opaque bytes that tell a neighbouring rank where this slab's planes and seam flags live."""
+        h = H.HsSlabHandle()
+        self._check(self._lib.hs_slab_export(self._ctx, C.byref(h)))
+        return bytes(h.bytes)
+
+    def slab_connect(self, up: bytes | None, down: bytes | None):
+        def conv(b):
+            if b is None:
+                return None
+            h = H.HsSlabHandle()
+            C.memmove(h.bytes, bytes(b), 256)
+            return C.byref(h)
+        self._check(self._lib.hs_slab_connect(self._ctx, conv(up), conv(down)))
 
     # -- plumbing ---------------------------------------------------------------------------
     def _check(self, rc):

@@ -11,13 +11,19 @@ HS_OK = 0
 HS_F32, HS_F64 = 0, 1
 FLAG_TOP_IS_SEAM, FLAG_BOTTOM_IS_SEAM, FLAG_FORCE_GENERIC, FLAG_SINGLE_PHASE, FLAG_TEXTBOOK = 1, 2, 4, 8, 16
 
+PREC_F32, PREC_F64 = 0, 1
+FRAME_U8, FRAME_S8, FRAME_U16, FRAME_S16, FRAME_S32, FRAME_F32, FRAME_F64 = range(7)
+DECOMP_BATCH, DECOMP_ROW_SLAB = 0, 1
+EXCHANGE_PEER, EXCHANGE_NCCL = 0, 1
+
 STATUS_NAMES = {0: "HS_OK", 1: "HS_ERR_INVALID_ARG", 2: "HS_ERR_CUDA", 3: "HS_ERR_OOM",
-                4: "HS_ERR_UNSUPPORTED", 5: "HS_ERR_STATE"}
+                4: "HS_ERR_UNSUPPORTED", 5: "HS_ERR_STATE", 6: "HS_ERR_NCCL"}
 
 # every extern "C" symbol include/hs.h declares (tests check the library exports all of them)
 SYMBOLS = ["hs_create", "hs_destroy", "hs_solve", "hs_solve_bgr", "hs_gradients", "hs_upload", "hs_prepare",
            "hs_iterate", "hs_iterate_rows", "hs_iterate_until", "hs_solve_device", "hs_download", "hs_sync", "hs_sample_grid", "hs_get_device_view",
-           "hs_video_push", "hs_video_flush", "hs_video_reset", "hs_get_timing", "hs_last_error", "hs_version", "hs_host_alloc", "hs_host_free"]
+           "hs_video_push", "hs_video_flush", "hs_video_reset", "hs_get_timing", "hs_last_error", "hs_version", "hs_host_alloc", "hs_host_free",
+           "hs_get_slab_info", "hs_plan_slab", "hs_slab_export", "hs_slab_connect"]
 
 
 class HsConfig(C.Structure):
@@ -25,7 +31,21 @@ class HsConfig(C.Structure):
                 ("window_size", C.c_int32), ("max_iterations", C.c_int32), ("alpha", C.c_double),
                 ("batch", C.c_int32), ("device", C.c_int32), ("temporal_k", C.c_int32),
                 ("flags", C.c_uint32), ("out_row_begin", C.c_int32), ("out_row_end", C.c_int32),
-                ("stream", C.c_void_p), ("global_row0", C.c_int32)]
+                ("stream", C.c_void_p), ("global_row0", C.c_int32),
+                ("precision", C.c_int32), ("frame_dtype", C.c_int32),
+                ("num_devices", C.c_int32), ("device_ids", C.POINTER(C.c_int32)),
+                ("decomposition", C.c_int32), ("exchange", C.c_int32),
+                ("slab_world", C.c_int32), ("slab_rank", C.c_int32)]
+
+
+class HsSlabInfo(C.Structure):
+    _fields_ = [("rank", C.c_int32), ("world", C.c_int32), ("own_begin", C.c_int32), ("own_end", C.c_int32),
+                ("buf_begin", C.c_int32), ("buf_end", C.c_int32), ("frame_begin", C.c_int32), ("frame_end", C.c_int32),
+                ("temporal_k", C.c_int32), ("halo_top", C.c_int32), ("halo_bottom", C.c_int32)]
+
+
+class HsSlabHandle(C.Structure):
+    _fields_ = [("bytes", C.c_uint8 * 256)]
 
 
 class HsTiming(C.Structure):
@@ -91,6 +111,10 @@ def load_library(path: str | None = None):
     lib.hs_version.argtypes = []
     lib.hs_host_alloc.argtypes = [C.POINTER(vp), sz]
     lib.hs_host_free.argtypes = [vp]
+    lib.hs_get_slab_info.argtypes = [vp, C.POINTER(HsSlabInfo)]
+    lib.hs_plan_slab.argtypes = [i32, i32, i32, i32, i32, C.POINTER(HsSlabInfo)]
+    lib.hs_slab_export.argtypes = [vp, C.POINTER(HsSlabHandle)]
+    lib.hs_slab_connect.argtypes = [vp, C.POINTER(HsSlabHandle), C.POINTER(HsSlabHandle)]
     for name in SYMBOLS:
         if name not in ("hs_destroy", "hs_last_error"):
             getattr(lib, name).restype = i32

@@ -15,7 +15,8 @@
  *   - plain C, no CUDA/torch/OpenCV types; every pointer is a raw host or device address
  *   - every function returns an hs_status (HS_OK == 0) and never throws; the text of the last
  *     failure is available from hs_last_error(ctx) (or hs_last_error(NULL) for hs_create)
- *   - a context is bound to one CUDA device and must not be used from two threads at once;
+ *   - a context is bound to one CUDA device (or to the devices listed in hs_config.device_ids) and
+ *     must not be used from two threads at once;
  *     distinct contexts are independent; there is no global mutable state
  *   - there is NO CPU fallback: without a usable CUDA device hs_create fails with HS_ERR_CUDA
  *   - images are row-major with a byte stride ("step" of cv::Mat); strides may exceed the row
@@ -40,7 +41,7 @@
 extern "C" {
 #endif
 
-#define HS_VERSION 100 /* 0.1.0 */
+#define HS_VERSION 200 /* 0.2.0 */
 
 typedef enum hs_status {
     HS_OK = 0,
@@ -48,10 +49,38 @@ typedef enum hs_status {
     HS_ERR_CUDA = 2,
     HS_ERR_OOM = 3,
     HS_ERR_UNSUPPORTED = 4,
-    HS_ERR_STATE = 5 /* call order violated, e.g. iterate before prepare */
+    HS_ERR_STATE = 5, /* call order violated, e.g. iterate before prepare */
+    HS_ERR_NCCL = 6   /* HS_EXCHANGE_NCCL: libnccl missing or an NCCL call failed */
 } hs_status;
 
 typedef enum hs_dtype { HS_F32 = 0, HS_F64 = 1 } hs_dtype;
+
+/* Arithmetic of the solve.  HS_PREC_F32 (default) is the fast path: exact integer gradients, fp32
+ * sweeps in the fused kernel, within 1e-4 px of the reference's fp64 result.  HS_PREC_F64 repeats the
+ * reference's own fp64 arithmetic operation by operation (convertTo(CV_64FC1) :23-24, every product
+ * and sum of :60-73 rounded separately, no contraction): BIT-IDENTICAL to the fp64 oracle for w <= 7.
+ * It is the A/B diagnostic for fp32 rounding and the path for frames that are not 8-bit. */
+typedef enum hs_precision { HS_PREC_F32 = 0, HS_PREC_F64 = 1 } hs_precision;
+
+/* Element type of the prev/next frames handed to hs_solve / hs_upload / hs_gradients (cv::Mat depths;
+ * the reference accepts any depth, hornSchunck.cpp:23-24).  Anything but HS_FRAME_U8 needs HS_PREC_F64. */
+typedef enum hs_frame_dtype {
+    HS_FRAME_U8 = 0, HS_FRAME_S8 = 1, HS_FRAME_U16 = 2, HS_FRAME_S16 = 3, HS_FRAME_S32 = 4, HS_FRAME_F32 = 5, HS_FRAME_F64 = 6
+} hs_frame_dtype;
+
+/* How one context spreads over several GPUs (hs_config.num_devices > 1, or slab_world > 1). */
+typedef enum hs_decomposition {
+    HS_DECOMP_BATCH = 0,    /* independent frame pairs: pair i runs on device i mod N, no communication        */
+    HS_DECOMP_ROW_SLAB = 1  /* ONE image cut into N bands of rows; k-row halos cross the seams every k sweeps  */
+} hs_decomposition;
+
+/* Row slabs: how the halo rows cross a seam. */
+typedef enum hs_exchange {
+    HS_EXCHANGE_PEER = 0, /* default: the fused kernel stores seam rows straight into the neighbour's halo rows
+                             (peer memory over NVLink) and signals per-tile flags; no host work between sweeps */
+    HS_EXCHANGE_NCCL = 1  /* A/B: one launch per k sweeps, ncclSend/ncclRecv of the halo rows in between
+                             (single process: ncclCommInitAll; libnccl is dlopen'ed, HS_ERR_NCCL if absent)     */
+} hs_exchange;
 
 /* hs_config.flags */
 #define HS_FLAG_TOP_IS_SEAM 0x1    /* row-slab: rows exist above this context's buffer          */
@@ -89,6 +118,24 @@ typedef struct hs_config {
     int32_t out_row_end;
     void* stream;           /* cudaStream_t to run on; NULL = a private non-blocking stream       */
     int32_t global_row0;    /* row slabs: image row of this context's buffer row 0 (default 0)    */
+    /* ---- fields added in 0.2 (struct_size tells the library whether they are present) --------- */
+    int32_t precision;      /* hs_precision                                                       */
+    int32_t frame_dtype;    /* hs_frame_dtype of the frames (default 8-bit unsigned)              */
+    /* Several GPUs behind ONE context, driven by the calling host thread (main.cpp:97-98 stays one
+     * call): num_devices > 1 makes hs_create build one child context per device.  hs_solve / hs_upload /
+     * hs_solve_device / hs_download / hs_sync / hs_get_timing work on such a context; the result is
+     * bit-identical to one GPU.  HS_DECOMP_BATCH deals the `batch` pairs to the devices; HS_DECOMP_ROW_SLAB
+     * (batch == 1, fused-kernel windows 2..9) splits the rows.  Listing the same ordinal several times
+     * runs that many row slabs on one GPU in a single launch (how the seam protocol is tested on 1 GPU). */
+    int32_t num_devices;        /* 0 or 1 = single device (`device`)                              */
+    const int32_t* device_ids;  /* num_devices ordinals; NULL = 0 .. num_devices-1                */
+    int32_t decomposition;      /* hs_decomposition                                               */
+    int32_t exchange;           /* hs_exchange (row slabs)                                        */
+    /* One PROCESS per GPU (torchrun / MPI style): this context is slab `slab_rank` of `slab_world` of an
+     * image `height` rows tall.  hs_get_slab_info says which frame rows to upload; neighbours are wired
+     * with hs_slab_export / hs_slab_connect (CUDA IPC), after which hs_iterate exchanges halos itself. */
+    int32_t slab_world;
+    int32_t slab_rank;
 } hs_config;
 
 typedef struct hs_ctx hs_ctx;
@@ -200,6 +247,34 @@ int hs_video_push(hs_ctx* ctx, const uint8_t* frame, size_t row_stride,
                   void* u, size_t u_row_stride, void* v, size_t v_row_stride, int out_dtype, int* pair_index);
 int hs_video_flush(hs_ctx* ctx, void* u, size_t u_row_stride, void* v, size_t v_row_stride, int* pair_index);
 int hs_video_reset(hs_ctx* ctx);
+
+/* ---- row slabs across processes (one rank per GPU) ------------------------------------------------ */
+/* Geometry of this context's slab inside the full image (valid for slab_world > 1 contexts and for
+ * the children of a row-slab group).  Rows are image rows. */
+typedef struct hs_slab_info {
+    int32_t rank, world;
+    int32_t own_begin, own_end;     /* rows this slab produces                                       */
+    int32_t buf_begin, buf_end;     /* rows its flow planes hold (own rows + halo)                   */
+    int32_t frame_begin, frame_end; /* rows of prev/next to pass to hs_upload (buffer + 1 Sobel row per seam) */
+    int32_t temporal_k;
+    int32_t halo_top, halo_bottom;  /* rows a neighbour writes into this slab per phase              */
+} hs_slab_info;
+int hs_get_slab_info(hs_ctx* ctx, hs_slab_info* out);
+/* The same plan as pure host arithmetic (no device needed): bands of rows with even first rows, a*k (+1
+ * when odd) halo rows above and (w/2)*k below each seam, one more frame row per seam for the Sobel taps. */
+int hs_plan_slab(int32_t height, int32_t world, int32_t rank, int32_t window_size, int32_t temporal_k,
+                 hs_slab_info* out);
+
+/* Opaque, fixed-size, position-independent description of where a slab's flow planes and seam flags
+ * live: ship it to the neighbouring ranks by any means (an all-gather of 256 bytes). */
+typedef struct hs_slab_handle { uint8_t bytes[256]; } hs_slab_handle;
+int hs_slab_export(hs_ctx* ctx, hs_slab_handle* out);
+/* Wire this slab to the slab above (rank-1) and below (rank+1); pass NULL at the image border.  Opens
+ * the neighbours' memory (cudaIpcOpenMemHandle; same-process handles are used directly with peer
+ * access).  Afterwards hs_iterate(n) runs all n sweeps in ONE launch.  Every rank must (1) call
+ * hs_prepare, (2) synchronise and barrier with its neighbours, (3) call hs_iterate with the same n;
+ * and must not call hs_prepare again before the neighbours' hs_iterate has completed. */
+int hs_slab_connect(hs_ctx* ctx, const hs_slab_handle* up, const hs_slab_handle* down);
 
 /* ---- introspection --------------------------------------------------------------------------- */
 int hs_get_timing(const hs_ctx* ctx, hs_timing* out);

@@ -23,7 +23,7 @@ def test_library_exports_every_declared_symbol(pkg):
     assert set(names) == set(H.SYMBOLS), (names, H.SYMBOLS)
     for n in names:
         assert getattr(lib, n) is not None
-    assert lib.hs_version() == 100
+    assert lib.hs_version() == 200
 
 
 def test_library_is_built_for_sm_100a_only(pkg):
@@ -41,14 +41,17 @@ def test_ctypes_structs_match_the_header_layout(pkg, tmp_path):
     import subprocess
     from cpp_optical_flow_b200 import hs_ctypes as H
     src = tmp_path / "sz.c"
-    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "hs.h"\nint main(void){printf("%zu %zu %zu %zu %zu %zu\\n",'
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "hs.h"\nint main(void){printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\\n",'
                    'sizeof(hs_config), sizeof(hs_timing), sizeof(hs_device_view), offsetof(hs_config, alpha),'
-                   'offsetof(hs_config, stream), offsetof(hs_device_view, halo_rows_bottom));return 0;}\n')
+                   'offsetof(hs_config, stream), offsetof(hs_device_view, halo_rows_bottom), offsetof(hs_config, precision),'
+                   'offsetof(hs_config, device_ids), offsetof(hs_config, slab_rank), sizeof(hs_slab_info), sizeof(hs_slab_handle));return 0;}\n')
     exe = tmp_path / "sz"
     subprocess.run(["/usr/bin/gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
     got = [int(x) for x in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()]
     want = [ctypes.sizeof(H.HsConfig), ctypes.sizeof(H.HsTiming), ctypes.sizeof(H.HsDeviceView),
-            H.HsConfig.alpha.offset, H.HsConfig.stream.offset, H.HsDeviceView.halo_rows_bottom.offset]
+            H.HsConfig.alpha.offset, H.HsConfig.stream.offset, H.HsDeviceView.halo_rows_bottom.offset,
+            H.HsConfig.precision.offset, H.HsConfig.device_ids.offset, H.HsConfig.slab_rank.offset,
+            ctypes.sizeof(H.HsSlabInfo), ctypes.sizeof(H.HsSlabHandle)]
     assert got == want, (got, want)
 
 
@@ -120,3 +123,34 @@ def test_synthetic_generator_is_deterministic_and_slab_consistent(pkg):
     part_a, part_b = s.frame_pair(30, 128, seed=5, y0=40)
     assert np.array_equal(part_a, a[40:70]) and np.array_equal(part_b, b[40:70])
     assert a.std() > 10 and not np.array_equal(a, b)
+
+
+def test_slab_plan_is_pure_host_arithmetic(pkg):
+    """hs_plan_slab (no GPU needed): bands tile the image, first rows are even, halos follow the anchor
+    of hornSchunck.cpp:54 (a*k rows above - rounded up to even - and (w/2)*k below), one Sobel row per seam."""
+    from cpp_optical_flow_b200 import hs_ctypes as H
+    lib = pkg.load_library()
+    for height, world, w, k in [(16384, 8, 3, 6), (1080, 4, 5, 3), (1081, 3, 4, 2), (375, 2, 2, 5), (97, 5, 3, 1), (4096, 8, 7, 2)]:
+        a = w - w // 2 - 1
+        rl, rr = a, w - 1 - a
+        prev_end = 0
+        for r in range(world):
+            info = H.HsSlabInfo()
+            assert lib.hs_plan_slab(height, world, r, w, k, ctypes.byref(info)) == 0
+            assert info.own_begin == prev_end and info.own_begin % 2 == 0 and info.own_end > info.own_begin
+            prev_end = info.own_end
+            top, bot = r > 0, r < world - 1
+            assert info.buf_begin == info.own_begin - ((rl * k + 1) // 2 * 2 if top else 0)
+            assert info.buf_end == info.own_end + (rr * k if bot else 0)
+            assert info.frame_begin == info.buf_begin - (1 if top else 0) and info.frame_end == info.buf_end + (1 if bot else 0)
+            assert info.frame_begin >= 0 and info.frame_end <= height
+            assert (info.halo_top, info.halo_bottom) == (rl * k if top else 0, rr * k if bot else 0)
+        assert prev_end == height
+        sizes = []
+        for r in range(world):
+            info = H.HsSlabInfo(); lib.hs_plan_slab(height, world, r, w, k, ctypes.byref(info))
+            sizes.append(info.own_end - info.own_begin)
+        assert max(sizes) - min(sizes) <= 3
+    info = H.HsSlabInfo()
+    assert lib.hs_plan_slab(40, 8, 0, 3, 6, ctypes.byref(info)) == 1      # 5-row slabs cannot hold a 6-row halo
+    assert b"halo" in lib.hs_last_error(None)

@@ -378,6 +378,55 @@ def test_row_slabs_equal_single_solve(pkg, w, k, nslab, depth):
     assert np.array_equal(u, su) and np.array_equal(v, sv)
 
 
+@pytest.mark.parametrize("w,k,nslab,shape,iters", [
+    (3, 4, 2, (260, 300), 14), (3, 6, 3, (400, 517), 31), (5, 3, 2, (300, 260), 11), (5, 2, 4, (333, 700), 9),
+    (4, 2, 3, (270, 200), 7), (2, 4, 2, (200, 333), 13), (7, 2, 2, (280, 300), 5), (3, 4, 4, (1080, 1920), 60),
+    (3, 0, 2, (1080, 1920), 100), (5, 0, 3, (900, 1600), 33), (3, 1, 2, (97, 150), 5)])
+def test_row_slab_group_in_kernel_exchange_equals_single_solve(pkg, w, k, nslab, shape, iters):
+    """ONE context over N row slabs (hs_config.num_devices, HS_DECOMP_ROW_SLAB) with the in-kernel halo
+    exchange: seam tiles store straight into the neighbour's halo rows and signal per-tile flags.  Listing
+    the same device N times runs the N slabs in one cooperative launch, so the whole seam protocol (peer
+    stores, system-scope release/acquire flags, reversed tile order of odd slabs) runs on this one GPU.
+    Bit-identical to the plain solve, also for a second solve and for split hs_iterate calls."""
+    from cpp_optical_flow_b200 import hs_ctypes as H
+    a, b = rand_pair(shape, seed=w * 7 + nslab)
+    with pkg.Solver(shape[1], shape[0], w, iters, 1.0, temporal_k=k) as s:
+        u, v = s.solve(a, b, np.float32)
+        kk = s.timing().temporal_k
+    with pkg.Solver(shape[1], shape[0], w, iters, 1.0, temporal_k=k, devices=[0] * nslab,
+                    decomposition=H.DECOMP_ROW_SLAB) as g:
+        gu, gv = g.solve(a, b, np.float32)
+        assert g.timing().kernel_id == 1
+        assert np.array_equal(u, gu) and np.array_equal(v, gv), (np.abs(u - gu).max(), np.argwhere(u != gu)[:4])
+        gu2, gv2 = g.solve(b, a, np.float32)                   # the context is reusable
+        gu3, gv3 = g.solve(a, b, np.float64)
+        assert np.array_equal(gu3, u.astype(np.float64)) and np.array_equal(gv3, v.astype(np.float64))
+        g.upload(a, b); g.prepare()                           # seam flags are absolute phase counts: split calls
+        g.iterate(iters // 3); g.iterate(iters - iters // 3)
+        su, sv = g.download(np.float32)
+        if g.timing().temporal_k == kk:
+            assert np.array_equal(u, su) and np.array_equal(v, sv)
+        else:
+            assert np.abs(u - su).max() < 1e-4
+    with pkg.Solver(shape[1], shape[0], w, iters, 1.0, temporal_k=k) as s:
+        u2, v2 = s.solve(b, a, np.float32)
+    assert np.array_equal(u2, gu2) and np.array_equal(v2, gv2)
+
+
+def test_multi_device_context_argument_errors(pkg):
+    from cpp_optical_flow_b200 import hs_ctypes as H
+    with pytest.raises(H.HsError):                            # slabs thinner than their halo
+        pkg.Solver(64, 20, 3, 5, 1.0, temporal_k=6, devices=[0, 0, 0, 0], decomposition=H.DECOMP_ROW_SLAB)
+    with pytest.raises(H.HsError):                            # the generic kernel has no slab path
+        pkg.Solver(64, 200, 11, 5, 1.0, devices=[0, 0], decomposition=H.DECOMP_ROW_SLAB)
+    with pytest.raises(H.HsError):                            # batch split needs distinct devices
+        pkg.Solver(64, 64, 3, 5, 1.0, batch=2, devices=[0, 0], decomposition=H.DECOMP_BATCH)
+    with pkg.Solver(200, 260, 3, 5, 1.0, devices=[0, 0], decomposition=H.DECOMP_ROW_SLAB) as g:
+        with pytest.raises(H.HsError) as e:
+            g.iterate_rows(1, 0, 10, True)
+        assert e.value.status == 4
+
+
 def test_partial_row_launches_compose_to_a_full_launch(pkg):
     """hs_iterate_rows (the overlap helper of the row-slab path): strips + interior == one launch."""
     a, b = rand_pair((300, 260), 77)
