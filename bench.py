@@ -60,6 +60,25 @@ def measured_hbm_peak():
         return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def traffic_lookup(workload, window, k, pixel_iterations_per_launch, launch_seconds, peak):
+    """DRAM bytes of ONE launch of the dominant kernel from the committed ncu captures (profiles/traffic.json,
+    written by tools/traffic_merge.py: dram__bytes_read.sum + dram__bytes_write.sum per pixel-iteration for this
+    (workload, window, k)), scaled to the pixel-iterations of the benched launch.  None - never a stale
+    constant - when no capture exists for the configuration."""
+    try:
+        table = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+    except Exception:
+        return None, "no profiles/traffic.json", None
+    e = table.get(f"{workload}_w{window}_k{k}")
+    if not e:
+        return None, f"no ncu capture for {workload} w={window} k={k}", None
+    byts = e["dram_bytes_per_pixel_iteration"] * pixel_iterations_per_launch
+    gbs = byts / launch_seconds / 1e9
+    return (byts, f"profiles/traffic.json[{workload}_w{window}_k{k}]: ncu dram__bytes_read+write.sum of a "
+                  f"{e['sweeps']}-sweep launch = {e['dram_bytes_per_pixel_iteration']:.3f} B per pixel-iteration, scaled",
+            {"gbs": gbs, "frac_of_peak": gbs / peak, "algorithmic_over_dram_bytes": 32.0 / e["dram_bytes_per_pixel_iteration"]})
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
@@ -209,7 +228,27 @@ def run_ours(args, rank, local_rank, world):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     if args.workload == "slab16k":
         from cpp_optical_flow_b200 import slab
-        return slab.bench_slab(args, rank, local_rank, world, METRIC, ALGO_BYTES_PER_PIXEL_ITER, measured_hbm_peak)
+        with ClockSampler(local_rank) as clocks:
+            rec = slab.bench_slab_record(args, rank, local_rank, world, ALGO_BYTES_PER_PIXEL_ITER, measured_hbm_peak,
+                                         iterations=args.iters or None, steps=args.steps, exchange=args.slab_exchange,
+                                         clock_sampler=clocks)
+            time.sleep(0.05)
+        check = slab.slab_bit_identity_check(rank, local_rank=local_rank, world=world) if not args.no_slab_check else None
+        if rank == 0:
+            line = {"metric": METRIC, "value": rec["value"], "unit": "Mpixel-iter/s", "n_gpus": world, "steps": args.steps,
+                    "warmup": args.warmup, "ms_per_step": rec["ms_per_step"], "higher_is_better": True, "scaling": "strong",
+                    "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                    "config": {"workload": "slab16k: " + rec["workload"], "window": rec["window"], "alpha": 1.0,
+                               "iterations": rec["iterations"], "temporal_k": rec["temporal_k"], "parallelism": rec["exchange"],
+                               "halo_rows_per_exchange": rec["halo_rows_per_exchange"],
+                               "halo_bytes_per_exchange_per_seam": rec["halo_bytes_per_exchange_per_seam"],
+                               "exchanges_per_step": rec["exchanges_per_step"], "l2": rec["l2"]},
+                    "roofline": dict(rec["roofline"], traffic=None), "e2e": None, "gpu_launches": rec["gpu_launches"],
+                    "clocks": clocks.summary(), "slab_bit_identical": check}
+            print(json.dumps(line), flush=True)
+        if world > 1:
+            dist.destroy_process_group()
+        return
 
     if args.workload == "batch256":
         return run_batch256(args, rank, local_rank, world)
@@ -319,6 +358,32 @@ def run_ours(args, rank, local_rank, world):
         dist.all_reduce(st, op=dist.ReduceOp.MAX)
     stream_value = float(H) * W * T * (n_frames - 1) * world / float(st.item()) / 1e6
 
+    solver.close()
+    del flush, hp, hn, hu, hv
+    torch.cuda.empty_cache()
+
+    # ---- BASELINE configs[4] beside the headline: ONE 16384^2 pair in row slabs over the same N GPUs
+    #      (the only path with a real exchange step), plus a bit-identity check of that path --------
+    slab_rec = None
+    if args.workload == "1080p" and not args.no_slab and not args.textbook:
+        from cpp_optical_flow_b200 import slab
+        with ClockSampler(local_rank) as sclocks:
+            slab_rec = slab.bench_slab_record(args, rank, local_rank, world, ALGO_BYTES_PER_PIXEL_ITER, measured_hbm_peak,
+                                              steps=args.slab_steps, exchange=args.slab_exchange, clock_sampler=sclocks)
+            time.sleep(0.05)
+        check = slab.slab_bit_identity_check(rank, world, local_rank)
+        single = None
+        if world > 1:        # the same code on ONE GPU (rank 0), for the parallel efficiency of this very run
+            if rank == 0:
+                single = slab.bench_slab_record(args, 0, local_rank, 1, ALGO_BYTES_PER_PIXEL_ITER, measured_hbm_peak, steps=1)
+            dist.barrier()
+        if rank == 0:
+            slab_rec["clocks"] = sclocks.summary()
+            slab_rec["slab_bit_identical"] = check
+            v1 = single["value"] if single else slab_rec["value"]
+            slab_rec["single_gpu_value"] = v1
+            slab_rec["slab_parallel_efficiency"] = slab_rec["value"] / (world * v1)
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -329,13 +394,10 @@ def run_ours(args, rank, local_rank, world):
     it_s = float(np.mean(iter_ms)) / 1e3
     achieved = ALGO_BYTES_PER_PIXEL_ITER * H * W * T / it_s / 1e9
     sweep_launches = launches // args.steps - 1              # minus the gradient kernel
-    traffic = None
-    try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(f"{args.workload}_w{window}")
-    except Exception:
-        pass
+    traffic, traffic_src, dram = traffic_lookup(args.workload, window, tm.temporal_k, float(H) * W * T / max(sweep_launches, 1),
+                                                it_s / max(sweep_launches, 1), peak)
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "peak_source": peak_src,
+                "traffic": traffic, "traffic_source": traffic_src, "dram": dram, "peak_source": peak_src,
                 "kernel": "k_jacobi_tile" if tm.kernel_id == 1 else "k_jacobi_generic",
                 "launches_per_step": sweep_launches, "avg_launch_us": it_s / max(sweep_launches, 1) * 1e6,
                 "algorithmic_bytes_per_launch": ALGO_BYTES_PER_PIXEL_ITER * H * W * T / max(sweep_launches, 1),
@@ -370,6 +432,8 @@ def run_ours(args, rank, local_rank, world):
             "prepare_ms": float(np.mean(prep_ms)), "iterate_ms": float(np.mean(iter_ms))}
     if cpu:
         line["cpu_baseline"] = cpu
+    if slab_rec:
+        line["slab16k"] = slab_rec
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -472,6 +536,11 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline sample")
     ap.add_argument("--ref-iters", type=int, default=16, help="--impl reference: sweeps per step (bounded sample)")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-slab", action="store_true", help="skip the 16K^2 row-slab sub-record of the default run")
+    ap.add_argument("--slab-steps", type=int, default=2, help="timed 16K^2 solves of the sub-record")
+    ap.add_argument("--slab-exchange", default="peer", choices=["peer", "nccl"],
+                    help="row slabs: in-kernel exchange over peer memory (default) or NCCL send/recv between launches")
+    ap.add_argument("--no-slab-check", action="store_true")
     ap.add_argument("--textbook", action="store_true",
                     help="non-parity extra: cube gradients + weighted 3x3 average (HS_FLAG_TEXTBOOK); no CPU baseline")
     args = ap.parse_args()

@@ -57,8 +57,7 @@ struct hs_ctx {
     size_t fpitch = 0, fimg = 0;
     uint8_t* d_prev = nullptr;
     uint8_t* d_next = nullptr;
-    float* d_u[2] = {nullptr, nullptr};
-    float* d_v[2] = {nullptr, nullptr};
+    float2* d_uv[2] = {nullptr, nullptr};   // flow planes, {u, v} interleaved per pixel (packed-fp32 operands), ping-pong
     int cur = 0;
     uint32_t* d_cpk = nullptr;   // packed {Ix, Iy, It}
     int* d_done = nullptr;       // per-tile phase counters of a multi-phase launch
@@ -79,13 +78,12 @@ struct hs_ctx {
     int vid_dtype = -1;
     size_t bgr_pitch = 0;
 
-    CUtensorMap tm_u[2], tm_v[2], tm_cpk, tm_inv;
+    CUtensorMap tm_uv[2], tm_cpk, tm_inv;
     // Row-slab seams (multi-GPU): where each neighbouring slab lives.  Set by slab_link(); a linked
     // context runs all sweeps of hs_iterate in ONE launch and exchanges halos from inside the kernel.
     struct Seam {
         bool on = false;
-        float* u[2] = {nullptr, nullptr};   // the neighbour's planes (peer-mapped device memory)
-        float* v[2] = {nullptr, nullptr};
+        float2* uv[2] = {nullptr, nullptr};  // the neighbour's planes (peer-mapped device memory)
         int dy = 0;                         // my buffer row y is the neighbour's buffer row y + dy
         int* inbox = nullptr;               // the neighbour's inbox (it polls it; my seam tiles publish there)
         int nbr_rows = 0, nbr_parity = 0;   // the neighbour's produced rows and the image-row parity of its first one
@@ -93,7 +91,7 @@ struct hs_ctx {
     Seam up, dn;
     int* d_inbox = nullptr;      // [2][SEAM_JMAX][tiles_x]: phase counts published by the neighbours
     void* arena = nullptr;       // seam contexts: u[2], v[2] and the inbox live in ONE allocation (one IPC handle)
-    size_t arena_bytes = 0, inbox_off = 0, plane_off[4] = {0, 0, 0, 0};
+    size_t arena_bytes = 0, inbox_off = 0, plane_off[2] = {0, 0};
     void* ipc_up = nullptr;      // arenas of the neighbours opened with cudaIpcOpenMemHandle (multi-process)
     void* ipc_dn = nullptr;
     bool linked = false;
@@ -162,11 +160,11 @@ PFN_cuTensorMapEncodeTiled_v12000 tensor_map_encoder() {
 
 // rank-3 map over (x, y, pair) of a pitched plane; box = SX x SY x 1; OOB reads as zero
 int make_map(hs_ctx* c, CUtensorMap* m, void* base, CUtensorMapDataType dt, int esize, int box_x,
-             int box_y) {
+             int box_y, int per_px = 1) {
     auto enc = tensor_map_encoder();
     if (!enc) return fail(c, HS_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
-    cuuint64_t dims[3] = {(cuuint64_t)c->W, (cuuint64_t)c->H, (cuuint64_t)c->B};
-    cuuint64_t strides[2] = {(cuuint64_t)c->pitch * esize, (cuuint64_t)c->plane * esize};
+    cuuint64_t dims[3] = {(cuuint64_t)c->W * per_px, (cuuint64_t)c->H, (cuuint64_t)c->B};
+    cuuint64_t strides[2] = {(cuuint64_t)c->pitch * per_px * esize, (cuuint64_t)c->plane * per_px * esize};
     cuuint32_t box[3] = {(cuuint32_t)box_x, (cuuint32_t)box_y, 1};
     cuuint32_t estr[3] = {1, 1, 1};
     CUresult r = enc(m, dt, 3, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
@@ -230,8 +228,8 @@ struct Tile {
     static bool fill_slab(const hs_ctx* c, hs::SlabDesc& S, int k, int row0, int row1, int tile0, bool seams) {
         memset(&S, 0, sizeof S);
         for (int i = 0; i < 2; ++i) {
-            S.tm_u[i] = c->tm_u[i]; S.tm_v[i] = c->tm_v[i];
-            S.u[i] = c->d_u[i]; S.v[i] = c->d_v[i];
+            S.tm_uv[i] = c->tm_uv[i];
+            S.uv[i] = c->d_uv[i];
         }
         S.tm_cpk = c->tm_cpk; S.tm_inv = c->tm_inv;
         S.g = c->geom();
@@ -257,11 +255,11 @@ struct Tile {
                 const RowTiling nt = tiling(k, L.nbr_rows, L.nbr_parity);
                 if (nt.vy != t.vy || nt.jt > hs::SEAM_JMAX || nt.jb > hs::SEAM_JMAX) return false;   // tile columns AND pitch must agree
                 if (q == 0) {
-                    for (int i = 0; i < 2; ++i) { S.up_u[i] = L.u[i]; S.up_v[i] = L.v[i]; }
+                    for (int i = 0; i < 2; ++i) S.up_uv[i] = L.uv[i];
                     S.up_dy = L.dy; S.push_up = RR * k; S.up_j = nt.jb;
                     S.out_up = L.inbox + (size_t)1 * hs::SEAM_JMAX * tiles_x;   // I am "the slab below" for it
                 } else {
-                    for (int i = 0; i < 2; ++i) { S.dn_u[i] = L.u[i]; S.dn_v[i] = L.v[i]; }
+                    for (int i = 0; i < 2; ++i) S.dn_uv[i] = L.uv[i];
                     S.dn_dy = L.dy; S.push_dn = RL * k; S.dn_j = nt.jt;
                     S.out_dn = L.inbox;                                          // I am "the slab above" for it
                 }
@@ -447,12 +445,10 @@ int do_iterate(hs_ctx* c, int iters) {
             dim3 grid((c->W + 31) / 32, (c->oy1 - c->oy0 + 7) / 8, c->B);
             const float kf = 1.0f / (float)(c->w * c->w);
             if (c->textbook)
-                hs::k_jacobi_generic_tb<<<grid, block, 0, c->stream>>>(c->d_u[c->cur], c->d_v[c->cur], c->d_u[c->cur ^ 1],
-                                                                       c->d_v[c->cur ^ 1], c->d_cpk, c->d_inv, c->geom(),
-                                                                       (float)(c->alpha * c->alpha));
+                hs::k_jacobi_generic_tb<<<grid, block, 0, c->stream>>>(c->d_uv[c->cur], c->d_uv[c->cur ^ 1], c->d_cpk,
+                                                                       c->d_inv, c->geom(), (float)(c->alpha * c->alpha));
             else
-                hs::k_jacobi_generic<<<grid, block, 0, c->stream>>>(c->d_u[c->cur], c->d_v[c->cur], c->d_u[c->cur ^ 1],
-                                                                    c->d_v[c->cur ^ 1], c->d_cpk, c->d_inv,
+                hs::k_jacobi_generic<<<grid, block, 0, c->stream>>>(c->d_uv[c->cur], c->d_uv[c->cur ^ 1], c->d_cpk, c->d_inv,
                                                                     c->geom(), c->w, c->a, kf);
             e = cudaGetLastError();
             c->cur ^= 1;
@@ -472,22 +468,21 @@ int do_download(hs_ctx* c, void* u, size_t us, size_t uis, void* v, size_t vs, s
     if (us < c->W * es || vs < c->W * es) return fail(c, HS_ERR_INVALID_ARG, "output row stride smaller than a row");
     if (c->B > 1 && (uis < us * rows || vis < vs * rows))
         return fail(c, HS_ERR_INVALID_ARG, "output image stride smaller than one image");
-    const char* su;
-    const char* sv;
+    // the device keeps {u, v} interleaved; the caller gets two planes of out_dtype (K5 splits / widens)
+    const long long n = c->plane * c->B;
+    int rc = ensure_out(c, (size_t)n * 2 * es);
+    if (rc) return rc;
+    const char* su = static_cast<const char*>(c->d_out);
+    const char* sv = su + (size_t)n * es;
     if (dt == HS_F64) {
-        const long long n = c->plane * c->B;
-        int rc = ensure_out(c, (size_t)n * 2 * sizeof(double));
-        if (rc) return rc;
         double* o = static_cast<double*>(c->d_out);
-        hs::k_widen<<<148 * 8, 256, 0, c->stream>>>(c->d_u[c->cur], c->d_v[c->cur], o, o + n, n);
-        HS_CUDA(c, cudaGetLastError());
-        c->timing.launches += 1;
-        su = reinterpret_cast<const char*>(o);
-        sv = reinterpret_cast<const char*>(o + n);
+        hs::k_split<double><<<148 * 8, 256, 0, c->stream>>>(c->d_uv[c->cur], o, o + n, n);
     } else {
-        su = reinterpret_cast<const char*>(c->d_u[c->cur]);
-        sv = reinterpret_cast<const char*>(c->d_v[c->cur]);
+        float* o = static_cast<float*>(c->d_out);
+        hs::k_split<float><<<148 * 8, 256, 0, c->stream>>>(c->d_uv[c->cur], o, o + n, n);
     }
+    HS_CUDA(c, cudaGetLastError());
+    c->timing.launches += 1;
     for (int b = 0; b < c->B; ++b) {
         const size_t off = ((size_t)b * c->plane + (size_t)c->oy0 * c->pitch) * es;
         HS_CUDA(c, cudaMemcpy2DAsync(static_cast<char*>(u) + (size_t)b * uis, us, su + off, (size_t)c->pitch * es,
@@ -640,17 +635,16 @@ int create_single(const hs_config& cfg_in, hs_ctx** out) {
     HS_CREATE_CUDA(cudaMalloc(&c->d_next, c->fimg * c->B));
     {   // the four flow planes and the seam inbox share ONE allocation: a single memset zeroes the state
         // (:49-50), and a single IPC handle exposes everything a neighbouring slab writes to
-        const size_t pbytes = (npx * sizeof(float) + 255) / 256 * 256;
+        const size_t pbytes = (npx * sizeof(float2) + 255) / 256 * 256;
         const size_t ibytes = (size_t)2 * hs::SEAM_JMAX * (c->W / 32 + 2) * sizeof(int);
-        c->inbox_off = 4 * pbytes;
+        c->inbox_off = 2 * pbytes;
         c->arena_bytes = c->inbox_off + (ibytes + 255) / 256 * 256;
         HS_CREATE_CUDA(cudaMalloc(&c->arena, c->arena_bytes));
         char* base = static_cast<char*>(c->arena);
-        for (int i = 0; i < 4; ++i) c->plane_off[i] = (size_t)i * pbytes;
-        c->d_u[0] = reinterpret_cast<float*>(base + c->plane_off[0]);
-        c->d_v[0] = reinterpret_cast<float*>(base + c->plane_off[1]);
-        c->d_u[1] = reinterpret_cast<float*>(base + c->plane_off[2]);
-        c->d_v[1] = reinterpret_cast<float*>(base + c->plane_off[3]);
+        for (int i = 0; i < 2; ++i) {
+            c->plane_off[i] = (size_t)i * pbytes;
+            c->d_uv[i] = reinterpret_cast<float2*>(base + c->plane_off[i]);
+        }
         c->d_inbox = reinterpret_cast<int*>(base + c->inbox_off);
         c->max_ctas = env_int("HS_MAX_CTAS", 0);
     }
@@ -722,8 +716,8 @@ int create_single(const hs_config& cfg_in, hs_ctx** out) {
         c->kernel_id = 1;
         int rc;
         for (int i = 0; i < 2; ++i) {
-            if ((rc = make_map(c, &c->tm_u[i], c->d_u[i], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, TS0::SX, TS0::SY))) return bail(rc);
-            if ((rc = make_map(c, &c->tm_v[i], c->d_v[i], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, TS0::SX, TS0::SY))) return bail(rc);
+            // {u, v} interleaved: a float plane 2*W wide, box 2*SX floats (256 = the TMA box limit)
+            if ((rc = make_map(c, &c->tm_uv[i], c->d_uv[i], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, 2 * TS0::SX, TS0::SY, 2))) return bail(rc);
         }
         if ((rc = make_map(c, &c->tm_cpk, c->d_cpk, CU_TENSOR_MAP_DATA_TYPE_UINT32, 4, TS0::SX, TS0::SY))) return bail(rc);
         if ((rc = make_map(c, &c->tm_inv, c->d_inv, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, TS0::SX, TS0::SY))) return bail(rc);
@@ -842,8 +836,7 @@ int hs_iterate_until(hs_ctx* c, int max_sweeps, double tolerance, int check_ever
         if ((rc = do_iterate(c, 1))) return rc;
         done += chunk;
         HS_CUDA(c, cudaMemsetAsync(c->d_resid, 0, sizeof(unsigned int), c->stream));
-        hs::k_max_abs_diff<<<148 * 4, 256, 0, c->stream>>>(c->d_u[c->cur ^ 1], c->d_u[c->cur], c->d_v[c->cur ^ 1],
-                                                          c->d_v[c->cur], c->geom(), c->B, c->d_resid);
+        hs::k_max_abs_diff<<<148 * 4, 256, 0, c->stream>>>(c->d_uv[c->cur ^ 1], c->d_uv[c->cur], c->geom(), c->B, c->d_resid);
         HS_CUDA(c, cudaGetLastError());
         c->timing.launches += 1;
         unsigned int bits = 0;
@@ -1024,7 +1017,7 @@ int hs_sample_grid(hs_ctx* c, int delta, double* u, double* v, int* ny_out, int*
     int rc = ensure_out(c, n * 2 * sizeof(double));
     if (rc) return rc;
     double* o = static_cast<double*>(c->d_out);
-    hs::k_sample_grid<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(c->d_u[c->cur], c->d_v[c->cur], o, o + n,
+    hs::k_sample_grid<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(c->d_uv[c->cur], o, o + n,
                                                                        c->pitch, c->oy0, delta, ny, nx);
     HS_CUDA(c, cudaGetLastError());
     HS_CUDA(c, cudaMemcpyAsync(u, o, n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
@@ -1039,9 +1032,9 @@ int hs_get_device_view(hs_ctx* c, hs_device_view* o) {
     o->prev = c->d_prev; o->next = c->d_next;
     o->frame_pitch = c->fpitch; o->frame_pair_stride = c->fimg;
     o->frame_rows = c->frows; o->frame_row0 = c->frow0;
-    o->u = c->d_u[c->cur]; o->v = c->d_v[c->cur];
-    o->flow_pitch = (size_t)c->pitch * sizeof(float);
-    o->flow_pair_stride = (size_t)c->plane * sizeof(float);
+    o->uv = reinterpret_cast<float*>(c->d_uv[c->cur]); o->reserved = nullptr;
+    o->flow_pitch = (size_t)c->pitch * sizeof(float2);
+    o->flow_pair_stride = (size_t)c->plane * sizeof(float2);
     o->width = c->W; o->height = c->H; o->batch = c->B;
     o->halo_rows_top = c->RL * c->k;
     o->halo_rows_bottom = c->RR * c->k;
@@ -1170,14 +1163,13 @@ extern "C" int hs_video_push(hs_ctx* c, const uint8_t* frame, size_t stride, voi
     const long long npx = c->plane;
     if (dt == HS_F64) {
         double* o = static_cast<double*>(c->d_vout[p & 1]);
-        hs::k_widen<<<148 * 8, 256, 0, c->stream>>>(c->d_u[c->cur], c->d_v[c->cur], o, o + npx, npx);
-        HS_CUDA(c, cudaGetLastError());
-        c->timing.launches += 1;
+        hs::k_split<double><<<148 * 8, 256, 0, c->stream>>>(c->d_uv[c->cur], o, o + npx, npx);
     } else {
         float* o = static_cast<float*>(c->d_vout[p & 1]);
-        HS_CUDA(c, cudaMemcpyAsync(o, c->d_u[c->cur], npx * sizeof(float), cudaMemcpyDeviceToDevice, c->stream));
-        HS_CUDA(c, cudaMemcpyAsync(o + npx, c->d_v[c->cur], npx * sizeof(float), cudaMemcpyDeviceToDevice, c->stream));
+        hs::k_split<float><<<148 * 8, 256, 0, c->stream>>>(c->d_uv[c->cur], o, o + npx, npx);
     }
+    HS_CUDA(c, cudaGetLastError());
+    c->timing.launches += 1;
     HS_CUDA(c, cudaEventRecord(c->ev_solved[p & 1], c->stream));
     c->vid_frames = n + 1;            // committed only now: a failed step above leaves the sequence where it was
     c->vid_pending = p;

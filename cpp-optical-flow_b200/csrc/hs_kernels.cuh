@@ -226,77 +226,75 @@ k_grad_coeff_tb(const uint8_t* __restrict__ prev, const uint8_t* __restrict__ ne
 
 // K2 for the textbook mode: one weighted-average sweep, one pixel per thread
 __global__ void __launch_bounds__(256)
-k_jacobi_generic_tb(const float* __restrict__ u, const float* __restrict__ v,
-                    float* __restrict__ un, float* __restrict__ vn,
+k_jacobi_generic_tb(const float2* __restrict__ uv, float2* __restrict__ uvn,
                     const uint32_t* __restrict__ cpk, const float* __restrict__ itp, Geom g, float alpha2) {
     const int x = blockIdx.x * 32 + threadIdx.x;
     const int y = g.oy0 + blockIdx.y * 8 + threadIdx.y;
     if (x >= g.W || y >= g.oy1) return;
     const size_t base = (size_t)blockIdx.z * g.plane;
-    auto bar = [&](const float* P) {
-        auto tap = [&](int yy, int xx) {
-            return (yy >= 0 && yy < g.H && xx >= 0 && xx < g.W) ? P[(size_t)yy * g.pitch + xx] : 0.f;
-        };
-        auto h = [&](int yy) { return __fmaf_rn(2.f, tap(yy, x), __fadd_rn(tap(yy, x - 1), tap(yy, x + 1))); };
-        const float V = __fmaf_rn(2.f, h(y), __fadd_rn(h(y - 1), h(y + 1)));
-        return tb_bar(V, tap(y, x));
+    const float2* P = uv + base;
+    auto tap = [&](int yy, int xx) {
+        return (yy >= 0 && yy < g.H && xx >= 0 && xx < g.W) ? P[(size_t)yy * g.pitch + xx] : make_float2(0.f, 0.f);
     };
+    auto h = [&](int yy) {
+        const float2 l = tap(yy, x - 1), c = tap(yy, x), r = tap(yy, x + 1);
+        return make_float2(__fmaf_rn(2.f, c.x, __fadd_rn(l.x, r.x)), __fmaf_rn(2.f, c.y, __fadd_rn(l.y, r.y)));
+    };
+    const float2 hm = h(y - 1), h0 = h(y), hp = h(y + 1), ctr = tap(y, x);
+    const float Vu = __fmaf_rn(2.f, h0.x, __fadd_rn(hm.x, hp.x));
+    const float Vv = __fmaf_rn(2.f, h0.y, __fadd_rn(hm.y, hp.y));
     const size_t o = base + (size_t)y * g.pitch + x;
     float ix, iy, nu, nv;
     unpack_coef_tb(cpk[o], ix, iy);
-    hs_update_bar(bar(u + base), bar(v + base), ix, iy, itp[o], hs_inv(ix, iy, alpha2), nu, nv);
-    un[o] = nu;
-    vn[o] = nv;
+    hs_update_bar(tb_bar(Vu, ctr.x), tb_bar(Vv, ctr.y), ix, iy, itp[o], hs_inv(ix, iy, alpha2), nu, nv);
+    uvn[o] = make_float2(nu, nv);
 }
 
 // ------------------------------------------------------------------------------------------
 // K2: one Jacobi sweep, any window size (runtime w, anchor a).  One pixel per thread, taps read
 // through L1/L2.  This is the always-correct path (even / large windows, A/B reference for K3).
 // ------------------------------------------------------------------------------------------
+__device__ __forceinline__ float2 add2s(float2 a, float2 b) {      // two scalar IEEE adds (same rounding as FADD2)
+    return make_float2(__fadd_rn(a.x, b.x), __fadd_rn(a.y, b.y));
+}
 __global__ void __launch_bounds__(256)
-k_jacobi_generic(const float* __restrict__ u, const float* __restrict__ v,
-                 float* __restrict__ un, float* __restrict__ vn,
+k_jacobi_generic(const float2* __restrict__ uv, float2* __restrict__ uvn,
                  const uint32_t* __restrict__ cpk, const float* __restrict__ inv,
                  Geom g, int w, int a, float kf) {
     const int x = blockIdx.x * 32 + threadIdx.x;
     const int y = g.oy0 + blockIdx.y * 8 + threadIdx.y;
     if (x >= g.W || y >= g.oy1) return;
     const size_t base = (size_t)blockIdx.z * g.plane;
-    const float* U = u + base;
-    const float* V = v + base;
-    // canonical paired sums, written as plain loops (see the header comment)
-    auto row_sum = [&](const float* P, int yy) {            // sum over columns x-a .. x-a+w-1 of row yy
+    const float2* P = uv + base;
+    // canonical paired sums, written as plain loops (see the header comment); .x = u, .y = v
+    auto row_sum = [&](int yy) {                            // sum over columns x-a .. x-a+w-1 of row yy
         const bool yin = (yy >= 0) && (yy < g.H);
-        const float* row = P + (size_t)(yin ? yy : 0) * g.pitch;
-        auto tap = [&](int xx) { return (yin && xx >= 0 && xx < g.W) ? row[xx] : 0.f; };
+        const float2* row = P + (size_t)(yin ? yy : 0) * g.pitch;
+        auto tap = [&](int xx) { return (yin && xx >= 0 && xx < g.W) ? row[xx] : make_float2(0.f, 0.f); };
         int col = x - a;
         const int hi = col + w - 1;
-        float s = 0.f;
+        float2 s = make_float2(0.f, 0.f);
         bool first = true;
-        auto add = [&](float t) { s = first ? t : __fadd_rn(s, t); first = false; };
+        auto add = [&](float2 t) { s = first ? t : add2s(s, t); first = false; };
         if (col & 1) { add(tap(col)); ++col; }
-        for (; col + 1 <= hi; col += 2) add(__fadd_rn(tap(col), tap(col + 1)));
+        for (; col + 1 <= hi; col += 2) add(add2s(tap(col), tap(col + 1)));
         if (col == hi) add(tap(col));
         return s;
     };
-    auto box_sum = [&](const float* P) {                    // the same rule down the rows y-a .. y-a+w-1
-        int r = y - a;
-        const int hi = r + w - 1;
-        float s = 0.f;
-        bool first = true;
-        auto add = [&](float t) { s = first ? t : __fadd_rn(s, t); first = false; };
-        if ((r + g.grow0) & 1) { add(row_sum(P, r)); ++r; }
-        for (; r + 1 <= hi; r += 2) add(__fadd_rn(row_sum(P, r), row_sum(P, r + 1)));
-        if (r == hi) add(row_sum(P, r));
-        return s;
-    };
-    const float su = box_sum(U), sv = box_sum(V);
+    // the same rule down the rows y-a .. y-a+w-1
+    int r = y - a;
+    const int hi = r + w - 1;
+    float2 s = make_float2(0.f, 0.f);
+    bool first = true;
+    auto add = [&](float2 t) { s = first ? t : add2s(s, t); first = false; };
+    if ((r + g.grow0) & 1) { add(row_sum(r)); ++r; }
+    for (; r + 1 <= hi; r += 2) add(add2s(row_sum(r), row_sum(r + 1)));
+    if (r == hi) add(row_sum(r));
     const size_t o = base + (size_t)y * g.pitch + x;
     float ix, iy, it, nu, nv;
     unpack_coef(cpk[o], ix, iy, it);
-    hs_update(su, sv, kf, ix, iy, it, inv[o], nu, nv);
-    un[o] = nu;
-    vn[o] = nv;
+    hs_update(s.x, s.y, kf, ix, iy, it, inv[o], nu, nv);
+    uvn[o] = make_float2(nu, nv);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -424,9 +422,8 @@ struct TileShape {
                                                      //   only its first warp does anything)
     static constexpr int NSLOT = (RL + RR < R) ? (RL + RR) : R;       // patch rows a neighbour reads
     static constexpr size_t BYTES_F32 = (size_t)SX * SY * 4;
-    static constexpr size_t OFF_U = 0;                                // offsets inside one stage
-    static constexpr size_t OFF_V = OFF_U + BYTES_F32;
-    static constexpr size_t OFF_CPK = OFF_V + BYTES_F32;
+    static constexpr size_t OFF_UV = 0;                               // offsets inside one stage; uv = {u, v} interleaved
+    static constexpr size_t OFF_CPK = OFF_UV + 2 * BYTES_F32;
     static constexpr size_t OFF_INV = OFF_CPK + BYTES_F32;
     static constexpr size_t STAGE = OFF_INV + BYTES_F32;
     // exchange array [2 buf][2 field][NWARP][NSLOT][SX] floats, aliased onto the consumed stage
@@ -435,7 +432,10 @@ struct TileShape {
     static_assert(BYTES_EX <= STAGE, "exchange array must fit in one stage");
     static constexpr size_t OFF_BAR = 2 * STAGE;
     static constexpr size_t OFF_INFO = OFF_BAR + 64;                  // int4 x 2 x 2: decoded (x0, y0, pair, phase | slab, ...) of the staged items
-    static constexpr size_t SMEM = OFF_INFO + 64;                     // full[2], empty[2], stored[2]; item info
+    static constexpr size_t OFF_HOT = OFF_INFO + 64;                  // per-slab fields the compute warps read per tile
+    static constexpr size_t HOT_BYTES = 128;
+    static constexpr size_t SMEM_FOR(int maxs) { return OFF_HOT + HOT_BYTES * maxs; }
+    static constexpr size_t SMEM = SMEM_FOR(4);                       // full[2], empty[2], stored[2]; item info; hot
     static constexpr uint32_t TX_BYTES = (uint32_t)STAGE;
     // slot of patch row j in the exchange array (-1: no neighbour reads it)
     __host__ __device__ static constexpr int slot(int j) {
@@ -457,66 +457,97 @@ __host__ __device__ constexpr bool uses_term(bool pair, int pos) {
     return false;
 }
 
+// ---- packed fp32 (Blackwell FADD2 / FMUL2 / FFMA2) ---------------------------------------------
+// u and v go through IDENTICAL window sums, so the fused kernel carries them as one float2 per pixel
+// (.x = u, .y = v) and adds / scales both with one instruction.  Each half is rounded exactly like
+// the scalar __f*_rn form (IEEE round-to-nearest per lane), so the canonical arithmetic - and with
+// it bit-identity with k_jacobi_generic - is unchanged; only the instruction count drops
+// (13 -> 8 FP instructions per pixel-sweep for w=3).
+__device__ __forceinline__ float2 add2(float2 a, float2 b) { return __fadd2_rn(a, b); }
+__device__ __forceinline__ float2 shfl_up2(float2 a) {
+    return make_float2(__shfl_up_sync(0xffffffffu, a.x, 1), __shfl_up_sync(0xffffffffu, a.y, 1));
+}
+__device__ __forceinline__ float2 shfl_down2(float2 a) {
+    return make_float2(__shfl_down_sync(0xffffffffu, a.x, 1), __shfl_down_sync(0xffffffffu, a.y, 1));
+}
+// the per-pixel update on a packed average (hornSchunck.cpp:63-73), same operations as hs_update_bar:
+//   t = fma(Ix, ubar, fma(Iy, vbar, It));  c = t * inv;  {u', v'} = fma(-{Ix, Iy}, {c, c}, {ubar, vbar})
+__device__ __forceinline__ float2 hs_update_bar2(float2 bar, float2 ixy, float it, float inv) {
+    const float t = __fmaf_rn(ixy.x, bar.x, __fmaf_rn(ixy.y, bar.y, it));
+    const float c = __fmul_rn(t, inv);
+    return __ffma2_rn(make_float2(-ixy.x, -ixy.y), make_float2(c, c), bar);   // FFMA2 -R.F32x2, R.F32, R.F32x2
+}
+
 // Paired window sums of 4 consecutive positions 0..3 (position 0 is even in absolute terms).
 // s[i] = element at position i-4 (i = 0..11), p[i] = pair sum starting at position 2i-4 (i = 0..5);
 // only the entries uses_term() asks for have to be filled in.
 template <int RL, int RR>
-__device__ __forceinline__ void paired_sums(const float (&s)[12], const float (&p)[6], float (&out)[4]) {
+__device__ __forceinline__ void paired_sums(const float2 (&s)[12], const float2 (&p)[6], float2 (&out)[4]) {
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
         int x = c - RL;
         const int hi = c + RR;
-        float acc = 0.f;
+        float2 acc = make_float2(0.f, 0.f);
         bool first = true;
         if (x & 1) { acc = s[x + 4]; first = false; ++x; }
 #pragma unroll
         for (int i = 0; i < 4; ++i) {                 // at most 4 pairs in a window of <= 9
             if (x + 1 <= hi) {
-                acc = first ? p[(x + 4) / 2] : __fadd_rn(acc, p[(x + 4) / 2]);
+                acc = first ? p[(x + 4) / 2] : add2(acc, p[(x + 4) / 2]);
                 first = false;
                 x += 2;
             }
         }
-        if (x == hi) acc = first ? s[x + 4] : __fadd_rn(acc, s[x + 4]);
+        if (x == hi) acc = first ? s[x + 4] : add2(acc, s[x + 4]);
         out[c] = acc;
     }
 }
 
 // row sums of one patch row: the lane's 4 columns; neighbours' elements / pair sums by shuffle
 template <int RL, int RR>
-__device__ __forceinline__ void row_sums(const float (&a)[4], float (&h)[4]) {
-    float s[12], p[6];
+__device__ __forceinline__ void row_sums(const float2 (&a)[4], float2 (&h)[4]) {
+    float2 s[12], p[6];
 #pragma unroll
     for (int i = 0; i < 4; ++i) s[4 + i] = a[i];
     constexpr bool need_p0 = uses_term<RL, RR>(true, 0) || uses_term<RL, RR>(true, -4) || uses_term<RL, RR>(true, 4);
     constexpr bool need_p2 = uses_term<RL, RR>(true, 2) || uses_term<RL, RR>(true, -2) || uses_term<RL, RR>(true, 6);
-    if (need_p0) p[2] = __fadd_rn(a[0], a[1]);
-    if (need_p2) p[3] = __fadd_rn(a[2], a[3]);
+    if (need_p0) p[2] = add2(a[0], a[1]);
+    if (need_p2) p[3] = add2(a[2], a[3]);
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-        if (uses_term<RL, RR>(false, i - 4)) s[i] = __shfl_up_sync(0xffffffffu, a[i], 1);       // left lane's element i
-        if (uses_term<RL, RR>(false, i + 4)) s[8 + i] = __shfl_down_sync(0xffffffffu, a[i], 1);   // right lane's element i
+        if (uses_term<RL, RR>(false, i - 4)) s[i] = shfl_up2(a[i]);         // left lane's element i
+        if (uses_term<RL, RR>(false, i + 4)) s[8 + i] = shfl_down2(a[i]);   // right lane's element i
     }
-    if (uses_term<RL, RR>(true, -4)) p[0] = __shfl_up_sync(0xffffffffu, p[2], 1);
-    if (uses_term<RL, RR>(true, -2)) p[1] = __shfl_up_sync(0xffffffffu, p[3], 1);
-    if (uses_term<RL, RR>(true, 4)) p[4] = __shfl_down_sync(0xffffffffu, p[2], 1);
-    if (uses_term<RL, RR>(true, 6)) p[5] = __shfl_down_sync(0xffffffffu, p[3], 1);
+    if (uses_term<RL, RR>(true, -4)) p[0] = shfl_up2(p[2]);
+    if (uses_term<RL, RR>(true, -2)) p[1] = shfl_up2(p[3]);
+    if (uses_term<RL, RR>(true, 4)) p[4] = shfl_down2(p[2]);
+    if (uses_term<RL, RR>(true, 6)) p[5] = shfl_down2(p[3]);
     paired_sums<RL, RR>(s, p, h);
 }
 
 // row sums of the textbook mode: h = x[-1] + 2 x[0] + x[1]
-__device__ __forceinline__ void row_sums_tb(const float (&a)[4], float (&h)[4]) {
-    const float l = __shfl_up_sync(0xffffffffu, a[3], 1);
-    const float r = __shfl_down_sync(0xffffffffu, a[0], 1);
-    h[0] = __fmaf_rn(2.f, a[0], __fadd_rn(l, a[1]));
-    h[1] = __fmaf_rn(2.f, a[1], __fadd_rn(a[0], a[2]));
-    h[2] = __fmaf_rn(2.f, a[2], __fadd_rn(a[1], a[3]));
-    h[3] = __fmaf_rn(2.f, a[3], __fadd_rn(a[2], r));
+__device__ __forceinline__ void row_sums_tb(const float2 (&a)[4], float2 (&h)[4]) {
+    const float2 l = shfl_up2(a[3]);
+    const float2 r = shfl_down2(a[0]);
+    const float2 two = make_float2(2.f, 2.f);
+    h[0] = __ffma2_rn(two, a[0], add2(l, a[1]));
+    h[1] = __ffma2_rn(two, a[1], add2(a[0], a[2]));
+    h[2] = __ffma2_rn(two, a[2], add2(a[1], a[3]));
+    h[3] = __ffma2_rn(two, a[3], add2(a[2], r));
 }
 
+// One 256-bit store (Blackwell STG.E.ENL2.256): a lane's four {u, v} pixels = 32 contiguous bytes, a
+// warp's row = 1 KB with every 32-byte sector written whole by ONE instruction.  (Two 128-bit stores at a
+// 32-byte lane stride half-fill every sector twice: the store phase then runs at half the L1->L2 rate.)
+__device__ __forceinline__ void st_global_256(float2* dst, const float2 (&a)[4]) {
+    asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(dst), "f"(a[0].x), "f"(a[0].y),
+                 "f"(a[1].x), "f"(a[1].y), "f"(a[2].x), "f"(a[2].y), "f"(a[3].x), "f"(a[3].y)
+                 : "memory");
+}
+
+// k sweeps on a thread's 4 x R patch.  uv = {u, v} per pixel, gxy = {Ix, Iy}.
 template <int RL, int RR, int R, int NWARP, bool MASKED, bool TB>
-__device__ __forceinline__ void tile_sweeps(float (&u)[R][4], float (&v)[R][4],
-                                            const float (&ix)[R][4], const float (&iy)[R][4],
+__device__ __forceinline__ void tile_sweeps(float2 (&uv)[R][4], const float2 (&gxy)[R][4],
                                             const float (&it)[R][4], const float (&iv)[R][4],
                                             float* ex, int k, float kf, int warp, int lane,
                                             uint32_t inmask) {
@@ -525,122 +556,100 @@ __device__ __forceinline__ void tile_sweeps(float (&u)[R][4], float (&v)[R][4],
     // pixels of the invalid ring, so any finite-or-not value will do - read our own slots
     const int wa = warp > 0 ? warp - 1 : 0;
     const int wb = warp < NWARP - 1 ? warp + 1 : NWARP - 1;
+    const float2 kf2 = make_float2(kf, kf);
     for (int s = 0; s < k; ++s) {
-        float* exu = ex + (size_t)(s & 1) * 2 * TS::EX_FIELD;
-        float* exv = exu + TS::EX_FIELD;
-        float hu[R][4], hv[R][4];
+        // exchange array of this sweep parity: [NWARP][NSLOT][SX] float2 = {row sum of u, row sum of v}
+        float2* exs = reinterpret_cast<float2*>(ex) + (size_t)(s & 1) * TS::EX_FIELD;
+        float2 h[R][4];
 #pragma unroll
         for (int j = 0; j < R; ++j) {
-            if (TB) { row_sums_tb(u[j], hu[j]); row_sums_tb(v[j], hv[j]); }
-            else { row_sums<RL, RR>(u[j], hu[j]); row_sums<RL, RR>(v[j], hv[j]); }
+            if (TB) row_sums_tb(uv[j], h[j]);
+            else row_sums<RL, RR>(uv[j], h[j]);
             if (TS::slot(j) >= 0) {  // rows a vertical neighbour will need
-                const size_t o = ((size_t)warp * TS::NSLOT + TS::slot(j)) * TS::SX + lane * 4;
-                *reinterpret_cast<float4*>(exu + o) = make_float4(hu[j][0], hu[j][1], hu[j][2], hu[j][3]);
-                *reinterpret_cast<float4*>(exv + o) = make_float4(hv[j][0], hv[j][1], hv[j][2], hv[j][3]);
+                // a row is stored as two halves of 32 lanes x 16 B (pixels 0-1 of every lane, then pixels
+                // 2-3): consecutive lanes hit consecutive 16-byte chunks, no bank conflicts
+                float4* o = reinterpret_cast<float4*>(exs + ((size_t)warp * TS::NSLOT + TS::slot(j)) * TS::SX) + lane;
+                o[0] = make_float4(h[j][0].x, h[j][0].y, h[j][1].x, h[j][1].y);
+                o[32] = make_float4(h[j][2].x, h[j][2].y, h[j][3].x, h[j][3].y);
             }
         }
         static_assert(R == 4, "the shared column pairs below are (0,1) and (2,3)");
-        float qu[2][4], qv[2][4];                      // shared pair sums of the patch's own rows
+        float2 q[2][4];                                // shared pair sums of the patch's own rows
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
-            qu[0][c] = __fadd_rn(hu[0][c], hu[1][c]); qv[0][c] = __fadd_rn(hv[0][c], hv[1][c]);
-            qu[1][c] = __fadd_rn(hu[2][c], hu[3][c]); qv[1][c] = __fadd_rn(hv[2][c], hv[3][c]);
+            q[0][c] = add2(h[0][c], h[1][c]);
+            q[1][c] = add2(h[2][c], h[3][c]);
         }
         // one patch row: paired box sum down the column from the row sums of rows j-RL..j+RR (the
         // patch's first row is an even image row), then the update
-        auto column_term = [&](const float (&hh)[R][4], const float (&ab)[RL > 0 ? RL : 1][4],
-                               const float (&be)[RR > 0 ? RR : 1][4], int i, int c) {
-            return i < 0 ? ab[i + RL][c] : (i >= R ? be[i - R][c] : hh[i][c]);
+        auto column_term = [&](const float2 (&ab)[RL > 0 ? RL : 1][4], const float2 (&be)[RR > 0 ? RR : 1][4], int i, int c) {
+            return i < 0 ? ab[i + RL][c] : (i >= R ? be[i - R][c] : h[i][c]);
         };
-        auto update_row = [&](int j, const float (&au)[RL > 0 ? RL : 1][4], const float (&av)[RL > 0 ? RL : 1][4],
-                              const float (&bu)[RR > 0 ? RR : 1][4], const float (&bv)[RR > 0 ? RR : 1][4]) {
-            if constexpr (TB) {   // weighted average: V = h[j-1] + 2 h[j] + h[j+1], ubar = V/12 - u/3
-#pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    const float Vu = __fmaf_rn(2.f, hu[j][c], __fadd_rn(column_term(hu, au, bu, j - 1, c), column_term(hu, au, bu, j + 1, c)));
-                    const float Vv = __fmaf_rn(2.f, hv[j][c], __fadd_rn(column_term(hv, av, bv, j - 1, c), column_term(hv, av, bv, j + 1, c)));
-                    float nu, nv;
-                    hs_update_bar(tb_bar(Vu, u[j][c]), tb_bar(Vv, v[j][c]), ix[j][c], iy[j][c], it[j][c], iv[j][c], nu, nv);
-                    if (MASKED) {
-                        const bool in = (inmask >> (j * 4 + c)) & 1u;
-                        nu = in ? nu : 0.f;
-                        nv = in ? nv : 0.f;
-                    }
-                    u[j][c] = nu;
-                    v[j][c] = nv;
-                }
-            } else {
+        auto update_row = [&](int j, const float2 (&ab)[RL > 0 ? RL : 1][4], const float2 (&be)[RR > 0 ? RR : 1][4]) {
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
-                float su = 0.f, sv = 0.f;
-                bool first = true;
-                int i = j - RL;
-                const int hi = j + RR;
-                if (i & 1) {
-                    su = column_term(hu, au, bu, i, c); sv = column_term(hv, av, bv, i, c);
-                    first = false; ++i;
-                }
+                float2 bar;
+                if constexpr (TB) {   // weighted average: V = h[j-1] + 2 h[j] + h[j+1], ubar = V/12 - u/3
+                    const float2 V = __ffma2_rn(make_float2(2.f, 2.f), h[j][c], add2(column_term(ab, be, j - 1, c), column_term(ab, be, j + 1, c)));
+                    bar = __ffma2_rn(V, make_float2(HS_TB_W12, HS_TB_W12), __fmul2_rn(uv[j][c], make_float2(HS_TB_W3, HS_TB_W3)));
+                } else {
+                    float2 sum = make_float2(0.f, 0.f);
+                    bool first = true;
+                    int i = j - RL;
+                    const int hi = j + RR;
+                    if (i & 1) { sum = column_term(ab, be, i, c); first = false; ++i; }
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    if (i + 1 <= hi) {
-                        // pair (i, i+1), i even: inside the patch it is one of the two shared sums
-                        float pu, pv;
-                        if (i == 0) { pu = qu[0][c]; pv = qv[0][c]; }
-                        else if (i == 2) { pu = qu[1][c]; pv = qv[1][c]; }
-                        else {
-                            pu = __fadd_rn(column_term(hu, au, bu, i, c), column_term(hu, au, bu, i + 1, c));
-                            pv = __fadd_rn(column_term(hv, av, bv, i, c), column_term(hv, av, bv, i + 1, c));
+                    for (int qq = 0; qq < 4; ++qq) {
+                        if (i + 1 <= hi) {
+                            // pair (i, i+1), i even: inside the patch it is one of the two shared sums
+                            float2 pr;
+                            if (i == 0) pr = q[0][c];
+                            else if (i == 2) pr = q[1][c];
+                            else pr = add2(column_term(ab, be, i, c), column_term(ab, be, i + 1, c));
+                            sum = first ? pr : add2(sum, pr);
+                            first = false;
+                            i += 2;
                         }
-                        su = first ? pu : __fadd_rn(su, pu);
-                        sv = first ? pv : __fadd_rn(sv, pv);
-                        first = false;
-                        i += 2;
                     }
+                    if (i == hi) {
+                        const float2 tt = column_term(ab, be, i, c);
+                        sum = first ? tt : add2(sum, tt);
+                    }
+                    bar = __fmul2_rn(sum, kf2);
                 }
-                if (i == hi) {
-                    const float tu = column_term(hu, au, bu, i, c), tv = column_term(hv, av, bv, i, c);
-                    su = first ? tu : __fadd_rn(su, tu);
-                    sv = first ? tv : __fadd_rn(sv, tv);
-                }
-                float nu, nv;
-                hs_update(su, sv, kf, ix[j][c], iy[j][c], it[j][c], iv[j][c], nu, nv);
+                float2 n = hs_update_bar2(bar, gxy[j][c], it[j][c], iv[j][c]);
                 if (MASKED) {
                     const bool in = (inmask >> (j * 4 + c)) & 1u;
-                    nu = in ? nu : 0.f;
-                    nv = in ? nv : 0.f;
+                    n.x = in ? n.x : 0.f;
+                    n.y = in ? n.y : 0.f;
                 }
-                u[j][c] = nu;
-                v[j][c] = nv;
-            }
+                uv[j][c] = n;
             }
         };
-        float au[RL > 0 ? RL : 1][4], av[RL > 0 ? RL : 1][4];
-        float bu[RR > 0 ? RR : 1][4], bv[RR > 0 ? RR : 1][4];
+        float2 ab[RL > 0 ? RL : 1][4], be[RR > 0 ? RR : 1][4];
         // rows whose window stays inside the patch need nothing from the neighbours: do them while
         // the exchange rows of the other warps are still on their way
 #pragma unroll
-        for (int j = RL; j < R - RR; ++j) update_row(j, au, av, bu, bv);
+        for (int j = RL; j < R - RR; ++j) update_row(j, ab, be);
         compute_sync<TS::CTHREADS>();
         // neighbour rows: the last RL rows of the patch above, the first RR rows of the patch below
 #pragma unroll
         for (int i = 0; i < RL; ++i) {
-            const size_t o = ((size_t)wa * TS::NSLOT + TS::slot(R - RL + i)) * TS::SX + lane * 4;
-            const float4 q = *reinterpret_cast<const float4*>(exu + o);
-            const float4 p = *reinterpret_cast<const float4*>(exv + o);
-            au[i][0] = q.x; au[i][1] = q.y; au[i][2] = q.z; au[i][3] = q.w;
-            av[i][0] = p.x; av[i][1] = p.y; av[i][2] = p.z; av[i][3] = p.w;
+            const float4* o = reinterpret_cast<const float4*>(exs + ((size_t)wa * TS::NSLOT + TS::slot(R - RL + i)) * TS::SX) + lane;
+            const float4 a0 = o[0], a1 = o[32];
+            ab[i][0] = make_float2(a0.x, a0.y); ab[i][1] = make_float2(a0.z, a0.w);
+            ab[i][2] = make_float2(a1.x, a1.y); ab[i][3] = make_float2(a1.z, a1.w);
         }
 #pragma unroll
         for (int i = 0; i < RR; ++i) {
-            const size_t o = ((size_t)wb * TS::NSLOT + TS::slot(i)) * TS::SX + lane * 4;
-            const float4 q = *reinterpret_cast<const float4*>(exu + o);
-            const float4 p = *reinterpret_cast<const float4*>(exv + o);
-            bu[i][0] = q.x; bu[i][1] = q.y; bu[i][2] = q.z; bu[i][3] = q.w;
-            bv[i][0] = p.x; bv[i][1] = p.y; bv[i][2] = p.z; bv[i][3] = p.w;
+            const float4* o = reinterpret_cast<const float4*>(exs + ((size_t)wb * TS::NSLOT + TS::slot(i)) * TS::SX) + lane;
+            const float4 a0 = o[0], a1 = o[32];
+            be[i][0] = make_float2(a0.x, a0.y); be[i][1] = make_float2(a0.z, a0.w);
+            be[i][2] = make_float2(a1.x, a1.y); be[i][3] = make_float2(a1.z, a1.w);
         }
 #pragma unroll
         for (int j = 0; j < R; ++j)
-            if (j < RL || j >= R - RR) update_row(j, au, av, bu, bv);
+            if (j < RL || j >= R - RR) update_row(j, ab, be);
     }
 }
 
@@ -691,9 +700,8 @@ struct FastDiv {
     __device__ __forceinline__ int div(int n) const { return d == 1 ? n : (int)(__umulhi((uint32_t)n, mul) >> shr); }
 };
 struct SlabDesc {
-    CUtensorMap tm_u[2], tm_v[2], tm_cpk, tm_inv;
-    float* u[2];
-    float* v[2];
+    CUtensorMap tm_uv[2], tm_cpk, tm_inv;   // tm_uv: the flow plane as a float plane 2*W wide ({u, v} interleaved)
+    float2* uv[2];
     Geom g;                    // oy0 / oy1 = the rows this launch produces
     int hyt, vy;               // halo rows above the stored centre of a tile; rows of the centre
     int tiles_y, ntiles;       // tile rows; tiles_x * tiles_y * batch
@@ -702,8 +710,8 @@ struct SlabDesc {
     int reverse;               // walk the tile rows bottom-up (odd slabs: both sides of a seam are then
                                //   processed at the same end of a phase, a whole phase before they are needed)
     // --- seams; null pointers = no neighbour on that side -----------------------------------
-    float* up_u[2]; float* up_v[2];   // the planes of the slab above / below (peer memory)
-    float* dn_u[2]; float* dn_v[2];
+    float2* up_uv[2];          // the planes of the slab above / below (peer memory)
+    float2* dn_uv[2];
     int up_dy, dn_dy;          // buffer row y of this slab is buffer row y + dy of that neighbour
     int push_up, push_dn;      // the first push_up / last push_dn produced rows are halo rows of the neighbour
     int* inbox;                // [2][SEAM_JMAX][tiles_x]: phase counts published by the slab above ([0]) / below ([1])
@@ -711,6 +719,20 @@ struct SlabDesc {
     int jt, jb;                // tile rows [0, jt) touch the seam above, [tiles_y - jb, tiles_y) the seam below
     int up_j, dn_j;            // flag rows to wait for in inbox[0] / inbox[1] (the neighbour's jb / jt); 0 = no seam
 };
+
+// What the compute warps need from a SlabDesc for every tile, copied to shared memory once per launch:
+// reading it from the kernel-parameter constant bank missed the constant cache about once per tile
+// (ncu: ~5 % of all stall samples on three LDCs of the store epilogue).
+struct SlabHot {
+    float2* uv[2];
+    float2* up_uv[2];
+    float2* dn_uv[2];
+    long long plane;
+    int W, H, pitch, oy0, oy1, hyt, vy;
+    int push_up, push_dn, up_dy, dn_dy;
+    int seam;                  // any neighbour to push rows to
+};
+static_assert(sizeof(SlabHot) <= 128, "SlabHot must fit HOT_BYTES");
 
 // geometry of one launch (host-computed)
 template <int MAXS>
@@ -849,6 +871,15 @@ k_jacobi_tile(const __grid_constant__ LaunchDesc<MAXS> d) {
         return it;
     };
 
+    if (tid < MAXS && tid < d.nslabs) {               // descriptor fields of the hot loop: constant bank -> shared memory
+        const SlabDesc& S = d.s[tid];
+        SlabHot h;
+        for (int i = 0; i < 2; ++i) { h.uv[i] = S.uv[i]; h.up_uv[i] = S.up_uv[i]; h.dn_uv[i] = S.dn_uv[i]; }
+        h.plane = S.g.plane; h.W = S.g.W; h.H = S.g.H; h.pitch = S.g.pitch; h.oy0 = S.g.oy0; h.oy1 = S.g.oy1;
+        h.hyt = S.hyt; h.vy = S.vy; h.push_up = S.push_up; h.push_dn = S.push_dn; h.up_dy = S.up_dy; h.dn_dy = S.dn_dy;
+        h.seam = (S.up_uv[0] != nullptr) || (S.dn_uv[0] != nullptr);
+        *reinterpret_cast<SlabHot*>(smem + TS::OFF_HOT + TS::HOT_BYTES * tid) = h;
+    }
     if (tid == 0) {
         mbar_init(&full[0], 1);
         mbar_init(&full[1], 1);
@@ -880,17 +911,14 @@ k_jacobi_tile(const __grid_constant__ LaunchDesc<MAXS> d) {
             mbar_expect_tx(&full[stage], TS::TX_BYTES);
             tma_load_3d(st + TS::OFF_CPK, &S.tm_cpk, &full[stage], it.x0, it.y0, it.b);
             tma_load_3d(st + TS::OFF_INV, &S.tm_inv, &full[stage], it.x0, it.y0, it.b);
-            tma_load_3d(st + TS::OFF_U, &S.tm_u[rd], &full[stage], it.x0, it.y0, it.b);
-            tma_load_3d(st + TS::OFF_V, &S.tm_v[rd], &full[stage], it.x0, it.y0, it.b);
+            tma_load_3d(st + TS::OFF_UV, &S.tm_uv[rd], &full[stage], 2 * it.x0, it.y0, it.b);
         };
         if (lane == 0) {
 #pragma unroll
             for (int q = 0; q < MAXS; ++q)
                 if (q < d.nslabs) {
-                    tma_prefetch_desc(&d.s[q].tm_u[0]);
-                    tma_prefetch_desc(&d.s[q].tm_v[0]);
-                    tma_prefetch_desc(&d.s[q].tm_u[1]);
-                    tma_prefetch_desc(&d.s[q].tm_v[1]);
+                    tma_prefetch_desc(&d.s[q].tm_uv[0]);
+                    tma_prefetch_desc(&d.s[q].tm_uv[1]);
                     tma_prefetch_desc(&d.s[q].tm_cpk);
                     tma_prefetch_desc(&d.s[q].tm_inv);
                 }
@@ -1045,8 +1073,7 @@ k_jacobi_tile(const __grid_constant__ LaunchDesc<MAXS> d) {
     for (int n = 0; n < items; ++n) {
         const int stage = n & 1;
         unsigned char* st = smem + (size_t)stage * TS::STAGE;
-        const float* s_u = reinterpret_cast<const float*>(st + TS::OFF_U);
-        const float* s_v = reinterpret_cast<const float*>(st + TS::OFF_V);
+        const float4* s_uv = reinterpret_cast<const float4*>(st + TS::OFF_UV);   // two pixels {u,v,u,v} per float4
         const uint32_t* s_cpk = reinterpret_cast<const uint32_t*>(st + TS::OFF_CPK);
         const float* s_inv = reinterpret_cast<const float*>(st + TS::OFF_INV);
 
@@ -1057,11 +1084,11 @@ k_jacobi_tile(const __grid_constant__ LaunchDesc<MAXS> d) {
         const int4 info = reinterpret_cast<const int4*>(smem + TS::OFF_INFO)[2 * stage];   // decoded by the producer
         const int tx0 = info.x, ty0 = info.y, b = info.z, cur_p = info.w;
         const int si = MAXS > 1 ? reinterpret_cast<const int4*>(smem + TS::OFF_INFO)[2 * stage + 1].x : 0;
-        const SlabDesc& S = d.s[si];
-        const Geom& g = S.g;
+        const SlabHot& S = *reinterpret_cast<const SlabHot*>(smem + TS::OFF_HOT + TS::HOT_BYTES * si);
+        const int gW = S.W, gH = S.H;
         const int gx0 = tx0 + lane * 4;
         const int gy0 = ty0 + row0;
-        const bool tile_inside = (tx0 >= 0) && (tx0 + TS::SX <= g.W) && (ty0 >= 0) && (ty0 + TS::SY <= g.H);
+        const bool tile_inside = (tx0 >= 0) && (tx0 + TS::SX <= gW) && (ty0 >= 0) && (ty0 + TS::SY <= gH);
         // which of the patch pixels lie inside the image (bit j*4+c); interior tiles never look at it
         uint32_t inmask = 0xffffffffu;
         if (!tile_inside) {
@@ -1070,35 +1097,35 @@ k_jacobi_tile(const __grid_constant__ LaunchDesc<MAXS> d) {
             for (int j = 0; j < R; ++j)
 #pragma unroll
                 for (int c = 0; c < 4; ++c) {
-                    const bool in = (gy0 + j >= 0) && (gy0 + j < g.H) && (gx0 + c >= 0) && (gx0 + c < g.W);
+                    const bool in = (gy0 + j >= 0) && (gy0 + j < gH) && (gx0 + c >= 0) && (gx0 + c < gW);
                     inmask |= (in ? 1u : 0u) << (j * 4 + c);
                 }
         }
 
-        float u[R][4], v[R][4], ix[R][4], iy[R][4], it[R][4], iv[R][4];
+        float2 uv[R][4], gxy[R][4];        // {u, v} and {Ix, Iy} per pixel: packed-fp32 operands
+        float it[R][4], iv[R][4];
 #pragma unroll
         for (int j = 0; j < R; ++j) {
             const int so = (row0 + j) * TS::SX + lane * 4;
-            const float4 qu = *reinterpret_cast<const float4*>(s_u + so);
-            const float4 qv = *reinterpret_cast<const float4*>(s_v + so);
+            const float4 q0 = s_uv[so / 2], q1 = s_uv[so / 2 + 1];
             const float4 qi = *reinterpret_cast<const float4*>(s_inv + so);
             const uint4 qc = *reinterpret_cast<const uint4*>(s_cpk + so);
-            u[j][0] = qu.x; u[j][1] = qu.y; u[j][2] = qu.z; u[j][3] = qu.w;
-            v[j][0] = qv.x; v[j][1] = qv.y; v[j][2] = qv.z; v[j][3] = qv.w;
+            uv[j][0] = make_float2(q0.x, q0.y); uv[j][1] = make_float2(q0.z, q0.w);
+            uv[j][2] = make_float2(q1.x, q1.y); uv[j][3] = make_float2(q1.z, q1.w);
             if (TB) {       // second plane = It; inv from the gradients
                 it[j][0] = qi.x; it[j][1] = qi.y; it[j][2] = qi.z; it[j][3] = qi.w;
-                unpack_coef_tb(qc.x, ix[j][0], iy[j][0]);
-                unpack_coef_tb(qc.y, ix[j][1], iy[j][1]);
-                unpack_coef_tb(qc.z, ix[j][2], iy[j][2]);
-                unpack_coef_tb(qc.w, ix[j][3], iy[j][3]);
+                unpack_coef_tb(qc.x, gxy[j][0].x, gxy[j][0].y);
+                unpack_coef_tb(qc.y, gxy[j][1].x, gxy[j][1].y);
+                unpack_coef_tb(qc.z, gxy[j][2].x, gxy[j][2].y);
+                unpack_coef_tb(qc.w, gxy[j][3].x, gxy[j][3].y);
 #pragma unroll
-                for (int c = 0; c < 4; ++c) iv[j][c] = hs_inv(ix[j][c], iy[j][c], d.alpha2);
+                for (int c = 0; c < 4; ++c) iv[j][c] = hs_inv(gxy[j][c].x, gxy[j][c].y, d.alpha2);
             } else {
                 iv[j][0] = qi.x; iv[j][1] = qi.y; iv[j][2] = qi.z; iv[j][3] = qi.w;
-                unpack_coef(qc.x, ix[j][0], iy[j][0], it[j][0]);
-                unpack_coef(qc.y, ix[j][1], iy[j][1], it[j][1]);
-                unpack_coef(qc.z, ix[j][2], iy[j][2], it[j][2]);
-                unpack_coef(qc.w, ix[j][3], iy[j][3], it[j][3]);
+                unpack_coef(qc.x, gxy[j][0].x, gxy[j][0].y, it[j][0]);
+                unpack_coef(qc.y, gxy[j][1].x, gxy[j][1].y, it[j][1]);
+                unpack_coef(qc.z, gxy[j][2].x, gxy[j][2].y, it[j][2]);
+                unpack_coef(qc.w, gxy[j][3].x, gxy[j][3].y, it[j][3]);
             }
         }
         // Everyone has (a) finished the previous tile - its exchange scratch in the OTHER stage is
@@ -1114,45 +1141,45 @@ k_jacobi_tile(const __grid_constant__ LaunchDesc<MAXS> d) {
         float* s_ex = reinterpret_cast<float*>(st);
         const int kk = min(d.k, d.sweeps - cur_p * d.k);
         if (tile_inside)
-            tile_sweeps<RL, RR, R, NWARP, false, TB>(u, v, ix, iy, it, iv, s_ex, kk, d.kf, warp, lane, inmask);
+            tile_sweeps<RL, RR, R, NWARP, false, TB>(uv, gxy, it, iv, s_ex, kk, d.kf, warp, lane, inmask);
         else
-            tile_sweeps<RL, RR, R, NWARP, true, TB>(u, v, ix, iy, it, iv, s_ex, kk, d.kf, warp, lane, inmask);
+            tile_sweeps<RL, RR, R, NWARP, true, TB>(uv, gxy, it, iv, s_ex, kk, d.kf, warp, lane, inmask);
 
         HS_PROF_T(pt3);
         // store the exact centre of the tile into the other pair of planes
         const int lx = lane * 4;
-        if (lx >= d.hxl && lx < d.hxl + d.vx && gx0 < g.W) {
+        const int seam = S.seam;
+        if (lx >= d.hxl && lx < d.hxl + d.vx && gx0 < gW) {
             const int wr = (d.cur ^ cur_p ^ 1) & 1;       // planes this phase writes
-            float* U = S.u[wr] + (size_t)b * g.plane;
-            float* V = S.v[wr] + (size_t)b * g.plane;
-            // row-slab seams: rows that are halo rows of a neighbouring slab also go straight into that
-            // slab's planes (peer memory over NVLink; all slabs flip their planes in lock step)
-            float* const UU = S.up_u[wr]; float* const VU = S.up_v[wr];
-            float* const UD = S.dn_u[wr]; float* const VD = S.dn_v[wr];
+            const int pitch = S.pitch, oy1 = S.oy1, hyt = S.hyt, ylim = S.hyt + S.vy;
+            float2* UV = S.uv[wr] + (size_t)b * S.plane;
 #pragma unroll
             for (int j = 0; j < R; ++j) {
                 const int ly = row0 + j;
                 const int gy = gy0 + j;
-                if (ly >= S.hyt && ly < S.hyt + S.vy && gy < g.oy1) {
-                    const size_t o = (size_t)gy * g.pitch + gx0;
-                    const float4 qu = make_float4(u[j][0], u[j][1], u[j][2], u[j][3]);
-                    const float4 qv = make_float4(v[j][0], v[j][1], v[j][2], v[j][3]);
-                    *reinterpret_cast<float4*>(U + o) = qu;
-                    *reinterpret_cast<float4*>(V + o) = qv;
-                    if (UU && gy < g.oy0 + S.push_up) {
-                        const size_t oo = (size_t)(gy + S.up_dy) * g.pitch + gx0;
-                        *reinterpret_cast<float4*>(UU + oo) = qu;
-                        *reinterpret_cast<float4*>(VU + oo) = qv;
-                    }
-                    if (UD && gy >= g.oy1 - S.push_dn) {
-                        const size_t oo = (size_t)(gy + S.dn_dy) * g.pitch + gx0;
-                        *reinterpret_cast<float4*>(UD + oo) = qu;
-                        *reinterpret_cast<float4*>(VD + oo) = qv;
+                if (ly >= hyt && ly < ylim && gy < oy1) {
+                    st_global_256(UV + (size_t)gy * pitch + gx0, uv[j]);
+                }
+            }
+            // row-slab seams: rows that are halo rows of a neighbouring slab also go straight into that
+            // slab's planes (peer memory over NVLink; all slabs flip their planes in lock step).  A
+            // CTA-uniform branch: tiles of a slab without neighbours never see this code.
+            if (seam) {
+                float2* const PU = S.up_uv[wr];
+                float2* const PD = S.dn_uv[wr];
+                const int up_lim = S.oy0 + S.push_up, dn_lim = oy1 - S.push_dn;
+#pragma unroll
+                for (int j = 0; j < R; ++j) {
+                    const int ly = row0 + j;
+                    const int gy = gy0 + j;
+                    if (ly >= hyt && ly < ylim && gy < oy1) {
+                        if (PU && gy < up_lim) st_global_256(PU + (size_t)(gy + S.up_dy) * pitch + gx0, uv[j]);
+                        if (PD && gy >= dn_lim) st_global_256(PD + (size_t)(gy + S.dn_dy) * pitch + gx0, uv[j]);
                     }
                 }
             }
         }
-        if (phases > 1 || S.out_up || S.out_dn) {   // tell the producer this warp's share of the tile is stored
+        if (phases > 1 || seam) {     // tell the producer this warp's share of the tile is stored
             __syncwarp();
             if (lane == 0) mbar_arrive(&stored[stage]);
         }
@@ -1166,14 +1193,16 @@ k_jacobi_tile(const __grid_constant__ LaunchDesc<MAXS> d) {
 // K5: outputs.  fp32 planes -> fp32/fp64 dense-ish host layout staging (pitch kept), and the
 // gradient planes back out of the packed coefficient layout.
 // ------------------------------------------------------------------------------------------
+// {u, v} interleaved -> two planes of T (double: the reference's CV_64FC1; float: plain split)
+template <typename T>
 __global__ void __launch_bounds__(256)
-k_widen(const float* __restrict__ a, const float* __restrict__ b2, double* __restrict__ oa,
-        double* __restrict__ ob, long long n) {
+k_split(const float2* __restrict__ uv, T* __restrict__ oa, T* __restrict__ ob, long long n) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long stride = (long long)gridDim.x * blockDim.x;
     for (long long p = i; p < n; p += stride) {
-        oa[p] = (double)a[p];
-        ob[p] = (double)b2[p];
+        const float2 q = uv[p];
+        oa[p] = (T)q.x;
+        ob[p] = (T)q.y;
     }
 }
 
@@ -1196,8 +1225,8 @@ k_unpack_grad_tb(const uint32_t* __restrict__ cpk, const float* __restrict__ itp
 // the residual of the early-exit extension.  Non-negative floats order like their bit patterns,
 // so the grid-wide maximum is an atomicMax on the raw bits; NaN counts as +inf.
 __global__ void __launch_bounds__(256)
-k_max_abs_diff(const float* __restrict__ a0, const float* __restrict__ a1, const float* __restrict__ b0,
-               const float* __restrict__ b1, Geom g, int batch, unsigned int* __restrict__ out) {
+k_max_abs_diff(const float2* __restrict__ p0, const float2* __restrict__ p1, Geom g, int batch,
+               unsigned int* __restrict__ out) {
     const int rows = g.oy1 - g.oy0;
     const long long per = (long long)rows * g.W;
     const long long n = per * batch;
@@ -1207,8 +1236,9 @@ k_max_abs_diff(const float* __restrict__ a0, const float* __restrict__ a1, const
         const long long r = i - (long long)b * per;
         const int y = g.oy0 + (int)(r / g.W), x = (int)(r % g.W);
         const size_t o = (size_t)b * g.plane + (size_t)y * g.pitch + x;
-        float d = fmaxf(fabsf(a1[o] - a0[o]), fabsf(b1[o] - b0[o]));
-        if (!(d == d) || !(a1[o] == a1[o]) || !(b1[o] == b1[o])) d = __int_as_float(0x7f800000);
+        const float2 q0 = p0[o], q1 = p1[o];
+        float d = fmaxf(fabsf(q1.x - q0.x), fabsf(q1.y - q0.y));
+        if (!(d == d) || !(q1.x == q1.x) || !(q1.y == q1.y)) d = __int_as_float(0x7f800000);
         m = fmaxf(m, d);
     }
 #pragma unroll
@@ -1219,14 +1249,15 @@ k_max_abs_diff(const float* __restrict__ a0, const float* __restrict__ a1, const
 // Flow samples on the plot grid: plotFlow::plotBresenhamLine reads u, v only at rows/columns that
 // are multiples of `delta` (plotFlow.cpp:70-75); this gathers just those (row-major grid order).
 __global__ void __launch_bounds__(256)
-k_sample_grid(const float* __restrict__ u, const float* __restrict__ v, double* __restrict__ ou,
+k_sample_grid(const float2* __restrict__ uv, double* __restrict__ ou,
               double* __restrict__ ov, int pitch, int row0, int delta, int ny, int nx) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= ny * nx) return;
     const int gy = i / nx, gx = i - gy * nx;
     const size_t o = (size_t)(row0 + gy * delta) * pitch + (size_t)gx * delta;
-    ou[i] = (double)u[o];
-    ov[i] = (double)v[o];
+    const float2 q = uv[o];
+    ou[i] = (double)q.x;
+    ov[i] = (double)q.y;
 }
 
 template <typename T>

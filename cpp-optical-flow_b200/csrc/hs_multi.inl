@@ -97,7 +97,7 @@ struct HandleBody {                 // what hs_slab_handle carries (<= 256 bytes
     uint32_t magic, version;
     int32_t pid, device;
     uint64_t arena_ptr;             // valid inside the exporting process only
-    uint64_t arena_bytes, inbox_off, plane_off[4];
+    uint64_t arena_bytes, inbox_off, plane_off[2];
     int32_t rank, world, width, window, k;
     int32_t b0, y0, y1;
     cudaIpcMemHandle_t ipc;
@@ -107,10 +107,8 @@ constexpr uint32_t HANDLE_MAGIC = 0x48535342u;   // "HSSB"
 
 void wire_seam(hs_ctx::Seam& L, const hs_ctx* me, const HandleBody& n, char* nbr_arena) {
     L.on = true;
-    L.u[0] = reinterpret_cast<float*>(nbr_arena + n.plane_off[0]);
-    L.v[0] = reinterpret_cast<float*>(nbr_arena + n.plane_off[1]);
-    L.u[1] = reinterpret_cast<float*>(nbr_arena + n.plane_off[2]);
-    L.v[1] = reinterpret_cast<float*>(nbr_arena + n.plane_off[3]);
+    L.uv[0] = reinterpret_cast<float2*>(nbr_arena + n.plane_off[0]);
+    L.uv[1] = reinterpret_cast<float2*>(nbr_arena + n.plane_off[1]);
     L.inbox = reinterpret_cast<int*>(nbr_arena + n.inbox_off);
     L.dy = me->sl_b0 - n.b0;
     L.nbr_rows = n.y1 - n.y0;
@@ -123,7 +121,7 @@ int export_handle(hs_ctx* c, HandleBody* h, bool want_ipc) {
     h->pid = (int32_t)getpid(); h->device = c->dev;
     h->arena_ptr = (uint64_t)(uintptr_t)c->arena;
     h->arena_bytes = c->arena_bytes; h->inbox_off = c->inbox_off;
-    for (int i = 0; i < 4; ++i) h->plane_off[i] = c->plane_off[i];
+    for (int i = 0; i < 2; ++i) h->plane_off[i] = c->plane_off[i];
     h->rank = c->slab_rank; h->world = c->slab_world; h->width = c->W; h->window = c->w; h->k = c->k;
     h->b0 = c->sl_b0; h->y0 = c->sl_y0; h->y1 = c->sl_y1;
     if (want_ipc) {
@@ -258,8 +256,8 @@ int nccl_exchange(hs_ctx* g) {
     for (int i = 0; i < n && r == 0; ++i) {
         hs_ctx* c = g->kids[i];
         const int up = c->RL * c->k, dn = c->RR * c->k;          // rows needed from above / below
-        const size_t rowf = (size_t)c->pitch;
-        float* planes[2] = {c->d_u[c->cur], c->d_v[c->cur]};
+        const size_t rowf = (size_t)c->pitch * 2;                // floats per row of the interleaved {u, v} plane
+        float* planes[1] = {reinterpret_cast<float*>(c->d_uv[c->cur])};
         for (float* P : planes) {
             if (i > 0) {                                          // seam above
                 if (dn && r == 0) r = st->Send(P + (size_t)c->oy0 * rowf, (size_t)dn * rowf, 7 /* ncclFloat */, i - 1, st->comms[i], c->stream);

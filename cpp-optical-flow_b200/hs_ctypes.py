@@ -57,7 +57,7 @@ class HsTiming(C.Structure):
 class HsDeviceView(C.Structure):
     _fields_ = [("prev", C.c_void_p), ("next", C.c_void_p), ("frame_pitch", C.c_size_t),
                 ("frame_pair_stride", C.c_size_t), ("frame_rows", C.c_int32), ("frame_row0", C.c_int32),
-                ("u", C.c_void_p), ("v", C.c_void_p), ("flow_pitch", C.c_size_t),
+                ("uv", C.c_void_p), ("reserved", C.c_void_p), ("flow_pitch", C.c_size_t),
                 ("flow_pair_stride", C.c_size_t), ("width", C.c_int32), ("height", C.c_int32),
                 ("batch", C.c_int32), ("halo_rows_top", C.c_int32), ("halo_rows_bottom", C.c_int32)]
 

@@ -171,15 +171,13 @@ class DeviceSlab:
         self.solver.upload(prev_rows, next_rows)
 
     def planes(self):
-        """torch views [rows, pitch] of the current u and v (they ping-pong between two buffers)."""
+        """[torch view [rows, 2 * pitch]] of the current flow plane ({u, v} interleaved per pixel; the two
+        planes ping-pong).  A halo is still a contiguous block of rows."""
         dv = self.solver.device_view()
-        out = []
-        for ptr in (dv.u, dv.v):
-            if ptr not in self._views:
-                pitch = dv.flow_pitch // 4
-                self._views[ptr] = self._torch.as_tensor(_DevMem(ptr, (dv.height, pitch)), device=self._device)
-            out.append(self._views[ptr])
-        return out
+        ptr = dv.uv
+        if ptr not in self._views:
+            self._views[ptr] = self._torch.as_tensor(_DevMem(ptr, (dv.height, dv.flow_pitch // 4)), device=self._device)
+        return [self._views[ptr]]
 
     def run(self, exchange=exchange_halos, group=None, overlap=True):
         """prepare + `iterations` sweeps; halos are exchanged after every `depth` fused launches.
@@ -274,7 +272,7 @@ def solve_slabs_single_process(prev, nxt, window, iterations, alpha, nslab, temp
                 views = [s.planes() for s in slabs]
                 for r in range(nslab - 1):               # seam between slab r (above) and r + 1 (below)
                     (a0, a1), (c0, c1) = geoms[r].out_rows, geoms[r + 1].out_rows
-                    for f in range(2):
+                    for f in range(len(views[r])):
                         if up:
                             views[r + 1][f][c0 - up:c0].copy_(views[r][f][a1 - up:a1])
                         if dn:
@@ -287,70 +285,209 @@ def solve_slabs_single_process(prev, nxt, window, iterations, alpha, nslab, temp
     return np.concatenate([p[0] for p in parts]), np.concatenate([p[1] for p in parts])
 
 
-def bench_slab(args, rank, local_rank, world, metric, algo_bytes, peak_fn):
-    """bench.py --workload slab16k: one 16384^2 pair, row slabs, halo exchange every k sweeps.
-    Strong scaling: total work is fixed, value = pixel-iterations of the whole image / max time."""
+class PeerSlab:
+    """One rank's row slab with the IN-KERNEL halo exchange (include/hs.h: slab_world / slab_rank,
+    hs_slab_export / hs_slab_connect).  This class is only a binding: the plan, the seam wiring (CUDA
+    IPC) and the exchange itself (peer stores + per-tile flags inside the fused kernel) live in
+    libhs_b200.so.  `all_gather(bytes) -> [bytes per rank]` is the only communication it needs."""
+
+    def __init__(self, height, width, window, iterations, alpha, rank, world, device, temporal_k=0, stream=None):
+        from .horn_schunck import Solver
+        self.rank, self.world, self.height, self.width = rank, world, height, width
+        self.solver = Solver(width, height, window, iterations, alpha, device=device, temporal_k=temporal_k,
+                             stream=stream, slab=(rank, world) if world > 1 else None)
+        if world > 1:
+            info = self.solver.slab_info()
+            self.own = (info.own_begin, info.own_end)
+            self.frame_rows = (info.frame_begin, info.frame_end)
+            self.halo = (info.halo_top, info.halo_bottom)
+        else:
+            self.own, self.frame_rows, self.halo = (0, height), (0, height), (0, 0)
+        self.k = self.solver.timing().temporal_k
+
+    def connect(self, all_gather):
+        if self.world == 1:
+            return
+        handles = all_gather(self.solver.slab_export())
+        self.solver.slab_connect(handles[self.rank - 1] if self.rank > 0 else None,
+                                 handles[self.rank + 1] if self.rank < self.world - 1 else None)
+
+    def close(self):
+        self.solver.close()
+
+
+def torch_all_gather_bytes(device):
+    """all_gather of a fixed-size bytes object through torch.distributed (NCCL needs device tensors)."""
+    import torch
+    import torch.distributed as dist
+
+    def gather(blob: bytes):
+        mine = torch.frombuffer(bytearray(blob), dtype=torch.uint8).to(device)
+        parts = [torch.empty_like(mine) for _ in range(dist.get_world_size())]
+        dist.all_gather(parts, mine)
+        return [bytes(p.cpu().numpy().tobytes()) for p in parts]
+    return gather
+
+
+def peer_slab_solve(prev_rows_fn, height, width, window, iterations, alpha, rank, world, local_rank, temporal_k=0):
+    """Solve one image over `world` ranks with the in-kernel exchange; returns this rank's (own rows, u, v)
+    as float32.  prev_rows_fn(f0, f1) -> (prev, next) uint8 rows [f0, f1) of the image."""
+    import torch
+    import torch.distributed as dist
+    dev = torch.device("cuda", local_rank)
+    s = PeerSlab(height, width, window, iterations, alpha, rank, world, local_rank, temporal_k)
+    try:
+        s.connect(torch_all_gather_bytes(dev))
+        a, b = prev_rows_fn(*s.frame_rows)
+        s.solver.upload(a, b)
+        s.solver.prepare()
+        s.solver.sync()
+        if world > 1:
+            dist.barrier()                    # every neighbour's planes and seam flags are zeroed
+        s.solver.iterate(iterations)
+        u, v = s.solver.download(np.float32)
+        if world > 1:
+            dist.barrier()
+        return s.own, u, v, s.k
+    finally:
+        s.close()
+
+
+def slab_bit_identity_check(rank, world, local_rank, size=2048, iterations=61, window=3):
+    """The multi-GPU result must equal the single-GPU result BIT FOR BIT: every rank solves its slab
+    of a size x size pair with the in-kernel exchange, rank 0 also solves the whole image alone."""
     import torch
     import torch.distributed as dist
     from . import synth
-    H = W = int(os.environ.get("HS_SLAB_SIZE", 16384))
-    T = args.iters or 5000
+    from .horn_schunck import Solver
+    own, u, v, k = peer_slab_solve(lambda f0, f1: synth.frame_pair(f1 - f0, size, y0=f0), size, size, window,
+                                   iterations, 1.0, rank, world, local_rank)
+    dev = torch.device("cuda", local_rank)
+    ok = None
+    if world == 1:
+        return {"size": size, "iterations": iterations, "window": window, "k": k, "bit_identical": True, "note": "one GPU"}
+    if rank == 0:
+        full_u = np.empty((size, size), np.float32); full_v = np.empty((size, size), np.float32)
+        full_u[own[0]:own[1]] = u; full_v[own[0]:own[1]] = v
+        y = own[1]
+        for r in range(1, world):
+            hdr = torch.empty(2, dtype=torch.int64, device=dev)
+            dist.recv(hdr, r)
+            y0, y1 = int(hdr[0]), int(hdr[1])
+            bu = torch.empty((y1 - y0, size), dtype=torch.float32, device=dev); bv = torch.empty_like(bu)
+            dist.recv(bu, r); dist.recv(bv, r)
+            full_u[y0:y1] = bu.cpu().numpy(); full_v[y0:y1] = bv.cpu().numpy()
+            assert y0 == y
+            y = y1
+        a, b = synth.frame_pair(size, size)
+        with Solver(size, size, window, iterations, 1.0, device=local_rank, temporal_k=k) as one:
+            ou, ov = one.solve(a, b, np.float32)
+        ok = bool(np.array_equal(ou, full_u) and np.array_equal(ov, full_v))
+        res = {"size": size, "iterations": iterations, "window": window, "k": k, "bit_identical": ok,
+               "max_abs_diff": float(max(np.abs(ou - full_u).max(), np.abs(ov - full_v).max()))}
+    else:
+        dist.send(torch.tensor(list(own), dtype=torch.int64, device=dev), 0)
+        dist.send(torch.from_numpy(u).to(dev), 0); dist.send(torch.from_numpy(v).to(dev), 0)
+        res = None
+    dist.barrier()
+    return res
+
+
+def bench_slab_record(args, rank, local_rank, world, algo_bytes, peak_fn, size=None, iterations=None, steps=2,
+                      exchange="peer", clock_sampler=None):
+    """BASELINE configs[4]: ONE 16384 x 16384 pair, 5000 sweeps, row slabs over the ranks (strong scaling).
+    Returns the record rank 0 prints (None on other ranks).  exchange = "peer": halos move inside the
+    fused kernel (stores into the neighbour's halo rows over NVLink + per-tile flags, one launch per
+    GPU for all sweeps); "nccl": one launch per k sweeps and torch.distributed send/recv in between
+    (the A/B the north star names)."""
+    import torch
+    import torch.distributed as dist
+    from . import synth
+    H = W = int(size or os.environ.get("HS_SLAB_SIZE", 16384))
+    T = int(iterations or 5000)
     window = args.window
     rl, rr = radii(window)
-    k = args.k or max(1, 6 // max(1, max(rl, rr)))
-    depth = int(os.environ.get("HS_SLAB_DEPTH", 0)) or (3 if world >= 8 else (2 if world >= 4 else 1))
-    geom = plan(H, W, world, rank, window, k, depth)
     dev = torch.device("cuda", local_rank)
-    prev, nxt = synth.frame_pair(geom.f1 - geom.f0, W, y0=geom.f0)
-    slab = DeviceSlab(geom, T, 1.0, local_rank)
-    slab.upload(prev, nxt)
-    slab.solver.sync()
-    flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
+    stream = torch.cuda.Stream(device=dev)
 
     def barrier():
         if world > 1:
             dist.barrier()
 
-    warm_T = min(T, 8 * k)
-    slab.iterations = warm_T
-    for _ in range(args.warmup):
-        slab.run(); torch.cuda.synchronize()
-    slab.iterations = T
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    if exchange == "nccl" and world > 1:
+        k = args.k or max(1, 6 // max(1, max(rl, rr)))
+        depth = int(os.environ.get("HS_SLAB_DEPTH", 0)) or (3 if world >= 8 else (2 if world >= 4 else 1))
+        geom = plan(H, W, world, rank, window, k, depth)
+        prev, nxt = synth.frame_pair(geom.f1 - geom.f0, W, y0=geom.f0)
+        old = DeviceSlab(geom, T, 1.0, local_rank)
+        old.upload(prev, nxt); old.solver.sync()
+        run_stream = old.stream
+
+        def run(iters):
+            old.iterations = iters
+            return old.run() + 1
+        halo_rows = (rl * k * depth, rr * k * depth)
+        exchanges = (T + k * depth - 1) // (k * depth) - 1
+        closer = old.close
+        how = f"NCCL send/recv between launches (torch.distributed), halo depth {depth} launches"
+    else:
+        ps = PeerSlab(H, W, window, T, 1.0, rank, world, local_rank, args.k, stream=stream.cuda_stream)
+        ps.connect(torch_all_gather_bytes(dev))
+        prev, nxt = synth.frame_pair(ps.frame_rows[1] - ps.frame_rows[0], W, y0=ps.frame_rows[0])
+        ps.solver.upload(prev, nxt); ps.solver.sync()
+        k = ps.k
+        run_stream = stream
+
+        def run(iters):
+            ps.solver.prepare()
+            if world > 1:
+                ps.solver.sync(); dist.barrier()      # neighbours' planes and seam flags are zeroed (inside the timed region)
+            ps.solver.iterate(iters)
+            return 2
+        halo_rows = (rl * k, rr * k)
+        exchanges = (T + k - 1) // k
+        closer = ps.close
+        how = ("in-kernel: seam tiles store their rows into the neighbour's halo rows over NVLink (peer memory, CUDA IPC) "
+               "and publish per-tile flags; one launch per GPU for all sweeps, no host work between sweeps")
+    del prev, nxt
+    flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
+    for _ in range(max(1, min(args.warmup, 2))):
+        run(min(T, 8 * k)); torch.cuda.synchronize(); barrier()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
     launches = 0
+    if clock_sampler is not None:
+        clock_sampler.mark()
     barrier(); torch.cuda.synchronize()
-    wall0 = time.perf_counter()
     for s, e in ev:
-        with torch.cuda.stream(slab.stream):
+        with torch.cuda.stream(run_stream):
             flush.zero_()
         torch.cuda.synchronize(); barrier()
-        s.record(slab.stream)
-        launches += slab.run() + 1
-        e.record(slab.stream)
-        torch.cuda.synchronize()
-    barrier()
-    wall = time.perf_counter() - wall0
+        s.record(run_stream)
+        launches += run(T)
+        e.record(run_stream)
+        torch.cuda.synchronize(); barrier()
     total = torch.tensor([sum(s.elapsed_time(e) for s, e in ev)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(total, op=dist.ReduceOp.MAX)
     total_s = float(total.item()) / 1e3
-    value = float(H) * W * T * args.steps / total_s / 1e6
-    if rank == 0:
-        peak, src = peak_fn()
-        achieved = algo_bytes * H * W * T * args.steps / total_s / 1e9 / world     # per GPU
-        line = {"metric": metric, "value": value, "unit": "Mpixel-iter/s", "n_gpus": world, "steps": args.steps,
-                "warmup": args.warmup, "ms_per_step": total_s / args.steps * 1e3, "higher_is_better": True,
-                "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": {"workload": f"slab16k: one {W}x{H} pair, {T} sweeps, row slabs", "window": window,
-                           "alpha": 1.0, "iterations": T, "temporal_k": k,
-                           "parallelism": f"{world} row slabs, {rl * k * depth}+{rr * k * depth} halo rows per seam "
-                                          f"every {k * depth} sweeps (halo depth {depth} launches)",
-                           "l2": "inputs (GBs per GPU) exceed L2; 512 MiB memset before every step anyway"},
-                "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                             "frac": achieved / peak, "traffic": None, "peak_source": src,
-                             "note": "per GPU, includes halo exchange time"},
-                "e2e": None, "gpu_launches": launches, "wall_ms_per_step": wall / args.steps * 1e3}
-        print(json.dumps(line), flush=True)
-    slab.close()
-    if world > 1:
-        dist.destroy_process_group()
+    closer()
+    del flush
+    torch.cuda.empty_cache()
+    if rank != 0:
+        return None
+    value = float(H) * W * T * steps / total_s / 1e6
+    peak, src = peak_fn()
+    achieved = algo_bytes * H * W * T * steps / total_s / 1e9 / world     # per GPU
+    return {"value": value, "unit": "Mpixel-iter/s", "ms_per_step": total_s / steps * 1e3, "steps": steps,
+            "scaling": "strong", "n_gpus": world,
+            "workload": f"configs[4]: one {W}x{H} pair, {T} sweeps, {world} row slab(s)", "window": window,
+            "iterations": T, "temporal_k": k, "exchange": how,
+            "halo_rows_per_exchange": {"from_above": halo_rows[0], "from_below": halo_rows[1]},
+            "halo_bytes_per_exchange_per_seam": int((halo_rows[0] + halo_rows[1]) * W * 4 * 2),
+            "exchanges_per_step": exchanges if world > 1 else 0,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "peak_source": src, "note": "per GPU, 32 algorithmic bytes per pixel-iteration, halo exchange included"},
+            "gpu_launches": launches,
+            "l2": "planes (GBs per GPU) exceed L2; 512 MiB memset before every step anyway"}
+
+

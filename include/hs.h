@@ -161,9 +161,11 @@ typedef struct hs_device_view {
     size_t frame_pair_stride; /* bytes between consecutive pairs of the batch                     */
     int32_t frame_rows;   /* height + (top seam ? 1 : 0) + (bottom seam ? 1 : 0)                  */
     int32_t frame_row0;   /* buffer row of the context's row 0 inside prev/next (0 or 1)          */
-    float* u;             /* CURRENT flow planes (they ping-pong: re-query after hs_iterate)       */
-    float* v;
-    size_t flow_pitch;    /* bytes per row of u / v                                               */
+    float* uv;            /* CURRENT flow plane, {u, v} INTERLEAVED per pixel (uv[2*x] = u, uv[2*x+1] = v):
+                             the fused kernel feeds both to Blackwell's packed-fp32 instructions.  The
+                             two planes ping-pong: re-query after hs_iterate                       */
+    void* reserved;
+    size_t flow_pitch;    /* bytes per row of uv (8 bytes per pixel)                              */
     size_t flow_pair_stride; /* bytes between pairs                                               */
     int32_t width, height, batch;
     int32_t halo_rows_top;    /* rows of halo a neighbour must refresh per fused launch: a*k      */

@@ -413,6 +413,39 @@ def test_row_slab_group_in_kernel_exchange_equals_single_solve(pkg, w, k, nslab,
     assert np.array_equal(u2, gu2) and np.array_equal(v2, gv2)
 
 
+def test_slab_rank_contexts_plan_export_and_connect(pkg):
+    """One process per GPU API (slab_world / slab_rank + hs_slab_export / hs_slab_connect): plan, handles and
+    wiring.  (Running two connected slabs as separate launches on ONE GPU is not allowed - kernels that wait
+    on each other must be co-resident - so the sweeps of this path are covered by the group context above
+    and, on real multi-GPU boxes, by bench.py's slab_bit_identical.)"""
+    from cpp_optical_flow_b200 import hs_ctypes as H
+    ranks = [pkg.Solver(300, 1000, 5, 30, 1.0, temporal_k=3, slab=(r, 3)) for r in range(3)]
+    try:
+        infos = [s.slab_info() for s in ranks]
+        assert [(i.own_begin, i.own_end) for i in infos] == [(0, 334), (334, 668), (668, 1000)]
+        assert [(i.buf_begin, i.buf_end) for i in infos] == [(0, 340), (328, 674), (662, 1000)]
+        assert [(i.frame_begin, i.frame_end) for i in infos] == [(0, 341), (327, 675), (661, 1000)]
+        assert all(i.temporal_k == 3 for i in infos) and (infos[1].halo_top, infos[1].halo_bottom) == (6, 6)
+        handles = [s.slab_export() for s in ranks]
+        assert all(len(h) == 256 for h in handles)
+        with pytest.raises(H.HsError):                        # a middle slab needs both neighbours
+            ranks[1].slab_connect(handles[0], None)
+        with pytest.raises(H.HsError):                        # wrong neighbour
+            ranks[1].slab_connect(handles[2], handles[0])
+        ranks[0].slab_connect(None, handles[1])
+        ranks[1].slab_connect(handles[0], handles[2])
+        ranks[2].slab_connect(handles[1], None)
+        with pytest.raises(H.HsError):
+            ranks[0].slab_connect(None, handles[1])           # already connected
+        a, b = rand_pair((1000, 300), 3)
+        ranks[1].upload(a[327:675], b[327:675])
+        with pytest.raises(ValueError):
+            ranks[1].upload(a, b)                             # wants exactly its frame rows
+    finally:
+        for s in ranks:
+            s.close()
+
+
 def test_multi_device_context_argument_errors(pkg):
     from cpp_optical_flow_b200 import hs_ctypes as H
     with pytest.raises(H.HsError):                            # slabs thinner than their halo

@@ -1,9 +1,15 @@
 #!/bin/bash
-# Multi-GPU session (gpurun --gpus N): slab correctness, weak-scaling batch bench, slab bench.
-N=${1:-2}; TAG=${2:-r01}
-TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511"
+# Multi-GPU session (gpurun --gpus N): slab correctness (in-kernel exchange), default bench (1080p replicas + the
+# 16K^2 row-slab sub-record), slab bench with both exchange variants.
+N=${1:-2}; TAG=${2:-r02}
+TR="timeout -s KILL 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511"
 mkdir -p gpurun_out
-echo "== slab check"; $TR tools/slab_check.py 4096 4096 51 3 6 2>&1 | grep -E "^\{|Error|error" | tee gpurun_out/${TAG}_slab_check_n$N.json
-$TR tools/slab_check.py 2048 3000 23 5 3 2>&1 | grep -E "^\{|Error|error" | tee -a gpurun_out/${TAG}_slab_check_n$N.json
-echo "== batch bench"; $TR bench.py --gpus $N --steps 5 --warmup 3 2>&1 | grep -E "^\{|Error|error" | tee gpurun_out/${TAG}_bench_1080p_n$N.json
-echo "== slab bench"; $TR bench.py --gpus $N --workload slab16k --steps 2 --warmup 1 --iters ${SLAB_ITERS:-600} 2>&1 | grep -E "^\{|Error|error" | tee gpurun_out/${TAG}_bench_slab16k_n$N.json
+nvidia-smi topo -m > gpurun_out/${TAG}_topo_n$N.txt 2>&1
+echo "== slab check (in-kernel exchange)"
+$TR tools/slab_check.py 4096 4096 51 3 6  2048 3000 23 5 3  3000 2048 40 4 2  4096 4096 400 3 0 2>&1 | grep -E "^\{|Error|error|Traceback" | tee gpurun_out/${TAG}_slab_check_n$N.json
+echo "== default bench (with slab16k sub-record)"
+$TR bench.py --gpus $N --steps 5 --warmup 3 > gpurun_out/${TAG}_bench_default_n$N.log 2>&1; grep -E "^\{" gpurun_out/${TAG}_bench_default_n$N.log > gpurun_out/${TAG}_bench_default_n$N.json; tail -c 2500 gpurun_out/${TAG}_bench_default_n$N.json; grep -E "Error|error|Traceback" gpurun_out/${TAG}_bench_default_n$N.log | head -5
+if [ "${SLAB_AB:-1}" = "1" ]; then
+echo "== slab bench: NCCL A/B"
+$TR bench.py --gpus $N --workload slab16k --steps 2 --warmup 1 --slab-exchange nccl --no-slab-check 2>&1 | grep -E "^\{|Error|error" | tee gpurun_out/${TAG}_bench_slab16k_nccl_n$N.json | cut -c1-600
+fi
