@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libhs_b200.so")
 SOURCES = [os.path.join(CSRC, "hs_api.cu")]
-DEPS = SOURCES + [os.path.join(CSRC, "hs_kernels.cuh"), os.path.join(CSRC, "hs_multi.inl"),
+DEPS = SOURCES + [os.path.join(CSRC, "hs_kernels.cuh"), os.path.join(CSRC, "hs_multi.inl"), os.path.join(CSRC, "hs_kernels_f64.cuh"),
                   os.path.join(os.path.dirname(HERE), "include", "hs.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-shared", "-Xcompiler", "-fPIC"]

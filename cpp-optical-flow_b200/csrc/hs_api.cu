@@ -15,6 +15,7 @@
 #include <vector>
 
 #include "hs_kernels.cuh"
+#include "hs_kernels_f64.cuh"
 
 namespace {
 
@@ -55,6 +56,10 @@ struct hs_ctx {
 
     int frows = 0, frow0 = 0;
     size_t fpitch = 0, fimg = 0;
+    // HS_PREC_F64 contexts (hs_kernels_f64.cuh): frames of any depth, every plane in fp64
+    bool f64 = false;
+    int fdt = HS_FRAME_U8, fes = 1;          // frame element type / size in bytes
+    double* d64[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // gx, gy, gt, den, u0, v0, u1, v1
     uint8_t* d_prev = nullptr;
     uint8_t* d_next = nullptr;
     float2* d_uv[2] = {nullptr, nullptr};   // flow planes, {u, v} interleaved per pixel (packed-fp32 operands), ping-pong
@@ -381,24 +386,29 @@ float ev_ms(cudaEvent_t a, cudaEvent_t b) {
 int do_upload(hs_ctx* c, const uint8_t* prev, size_t ps, size_t pis, const uint8_t* next, size_t ns,
               size_t nis) {
     if (!prev || !next) return fail(c, HS_ERR_INVALID_ARG, "null frame pointer");
-    if (ps < (size_t)c->W || ns < (size_t)c->W)
-        return fail(c, HS_ERR_INVALID_ARG, "row stride smaller than width");
+    if (ps < (size_t)c->W * c->fes || ns < (size_t)c->W * c->fes)
+        return fail(c, HS_ERR_INVALID_ARG, "row stride smaller than a row");
     if (c->B > 1 && (pis < ps * c->frows || nis < ns * c->frows))
         return fail(c, HS_ERR_INVALID_ARG, "image stride smaller than one image");
     if (c->d_ring[0]) { c->d_prev = c->d_ring[0]; c->d_next = c->d_ring[1]; }   // leave streaming mode
     for (int b = 0; b < c->B; ++b) {
         HS_CUDA(c, cudaMemcpy2DAsync(c->d_prev + (size_t)b * c->fimg, c->fpitch, prev + (size_t)b * pis, ps,
-                                     c->W, c->frows, cudaMemcpyHostToDevice, c->stream));
+                                     (size_t)c->W * c->fes, c->frows, cudaMemcpyHostToDevice, c->stream));
         HS_CUDA(c, cudaMemcpy2DAsync(c->d_next + (size_t)b * c->fimg, c->fpitch, next + (size_t)b * nis, ns,
-                                     c->W, c->frows, cudaMemcpyHostToDevice, c->stream));
+                                     (size_t)c->W * c->fes, c->frows, cudaMemcpyHostToDevice, c->stream));
     }
     c->uploaded = true;
     c->prepared = false;
     return HS_OK;
 }
 
+int f64_prepare(hs_ctx* c);
+int f64_iterate(hs_ctx* c, int iters);
+int f64_download(hs_ctx* c, void* u, size_t us, size_t uis, void* v, size_t vs, size_t vis, int dt);
+
 int do_prepare(hs_ctx* c) {
     if (!c->uploaded) return fail(c, HS_ERR_STATE, "hs_prepare before frames were uploaded");
+    if (c->f64) return f64_prepare(c);
     // u = v = 0 (hornSchunck.cpp:49-50): both plane pairs and the seam inbox are one allocation, one memset.
     // A linked row slab must not get here while a neighbour's previous hs_iterate is still running
     // (it stores into this arena): the group code orders that with events, separate processes barrier.
@@ -423,6 +433,7 @@ int do_prepare(hs_ctx* c) {
 int do_iterate(hs_ctx* c, int iters) {
     if (!c->prepared) return fail(c, HS_ERR_STATE, "hs_iterate before hs_prepare");
     if (iters < 0) return fail(c, HS_ERR_INVALID_ARG, "negative iteration count");
+    if (c->f64) return f64_iterate(c, iters);
     int left = iters;
     while (left > 0) {
         int step = 1;
@@ -466,6 +477,7 @@ int do_download(hs_ctx* c, void* u, size_t us, size_t uis, void* v, size_t vs, s
     const size_t es = dt == HS_F64 ? 8 : 4;
     const int rows = c->oy1 - c->oy0;
     if (us < c->W * es || vs < c->W * es) return fail(c, HS_ERR_INVALID_ARG, "output row stride smaller than a row");
+    if (c->f64) return f64_download(c, u, us, uis, v, vs, vis, dt);
     if (c->B > 1 && (uis < us * rows || vis < vs * rows))
         return fail(c, HS_ERR_INVALID_ARG, "output image stride smaller than one image");
     // the device keeps {u, v} interleaved; the caller gets two planes of out_dtype (K5 splits / widens)
@@ -491,6 +503,85 @@ int do_download(hs_ctx* c, void* u, size_t us, size_t uis, void* v, size_t vs, s
                                      c->W * es, rows, cudaMemcpyDeviceToHost, c->stream));
     }
     return HS_OK;
+}
+
+// ---- HS_PREC_F64 (hs_kernels_f64.cuh): reference arithmetic in fp64, frames of any depth -----------------
+template <typename T>
+void launch_grad_f64(hs_ctx* c) {
+    dim3 block(32, 8), grid((c->W + 31) / 32, (c->H + 7) / 8, c->B);
+    hs::k_grad_f64<T><<<grid, block, 0, c->stream>>>(reinterpret_cast<const T*>(c->d_prev), reinterpret_cast<const T*>(c->d_next),
+                                                     c->fpitch, c->fimg, c->d64[0], c->d64[1], c->d64[2], c->d64[3], c->W, c->H,
+                                                     c->pitch, c->plane, c->alpha * c->alpha);
+}
+
+int f64_prepare(hs_ctx* c) {
+    const size_t npx = (size_t)c->plane * c->B;
+    HS_CUDA(c, cudaMemsetAsync(c->d64[4], 0, npx * 4 * sizeof(double), c->stream));   // u = v = 0 (:49-50)
+    c->cur = 0;
+    switch (c->fdt) {
+        case HS_FRAME_U8: launch_grad_f64<uint8_t>(c); break;
+        case HS_FRAME_S8: launch_grad_f64<int8_t>(c); break;
+        case HS_FRAME_U16: launch_grad_f64<uint16_t>(c); break;
+        case HS_FRAME_S16: launch_grad_f64<int16_t>(c); break;
+        case HS_FRAME_S32: launch_grad_f64<int32_t>(c); break;
+        case HS_FRAME_F32: launch_grad_f64<float>(c); break;
+        default: launch_grad_f64<double>(c); break;
+    }
+    HS_CUDA(c, cudaGetLastError());
+    c->timing.launches += 1;
+    c->prepared = true;
+    return HS_OK;
+}
+
+int f64_iterate(hs_ctx* c, int iters) {
+    dim3 block(32, 8), grid((c->W + 31) / 32, (c->H + 7) / 8, c->B);
+    const double kf = 1.0 / (double)(c->w * c->w);                       // hornSchunck.cpp:53
+    for (int i = 0; i < iters; ++i) {
+        const int a = c->cur, b = c->cur ^ 1;
+        hs::k_jacobi_f64<<<grid, block, 0, c->stream>>>(c->d64[4 + 2 * a], c->d64[5 + 2 * a], c->d64[4 + 2 * b], c->d64[5 + 2 * b],
+                                                        c->d64[0], c->d64[1], c->d64[2], c->d64[3], c->W, c->H, c->pitch,
+                                                        c->plane, c->w, c->a, kf);
+        c->cur ^= 1;
+        c->timing.launches += 1;
+    }
+    HS_CUDA(c, cudaGetLastError());
+    return HS_OK;
+}
+
+int f64_copy_out(hs_ctx* c, const double* const* planes, int n, void* const* outs, size_t os, size_t ois, int dt) {
+    const size_t es = dt == HS_F64 ? 8 : 4;
+    const long long npx = c->plane * c->B;
+    for (int i = 0; i < n; ++i) {
+        const char* src = reinterpret_cast<const char*>(planes[i]);
+        if (dt == HS_F32) {
+            int rc = ensure_out(c, (size_t)npx * n * sizeof(float));
+            if (rc) return rc;
+            float* o = static_cast<float*>(c->d_out) + (size_t)i * npx;
+            hs::k_narrow_f64<<<148 * 8, 256, 0, c->stream>>>(planes[i], o, npx);
+            HS_CUDA(c, cudaGetLastError());
+            c->timing.launches += 1;
+            src = reinterpret_cast<const char*>(o);
+        }
+        for (int b = 0; b < c->B; ++b)
+            HS_CUDA(c, cudaMemcpy2DAsync(static_cast<char*>(outs[i]) + (size_t)b * ois, os, src + (size_t)b * c->plane * es,
+                                         (size_t)c->pitch * es, c->W * es, c->H, cudaMemcpyDeviceToHost, c->stream));
+    }
+    return HS_OK;
+}
+
+int f64_download(hs_ctx* c, void* u, size_t us, size_t uis, void* v, size_t vs, size_t vis, int dt) {
+    if (us != vs || uis != vis) {
+        const double* pu[1] = {c->d64[4 + 2 * c->cur]};
+        const double* pv[1] = {c->d64[5 + 2 * c->cur]};
+        void* ou[1] = {u}; void* ov[1] = {v};
+        int rc = f64_copy_out(c, pu, 1, ou, us, uis, dt);
+        if (rc) return rc;
+        HS_CUDA(c, cudaStreamSynchronize(c->stream));                     // the narrow staging is reused
+        return f64_copy_out(c, pv, 1, ov, vs, vis, dt);
+    }
+    const double* p[2] = {c->d64[4 + 2 * c->cur], c->d64[5 + 2 * c->cur]};
+    void* o[2] = {u, v};
+    return f64_copy_out(c, p, 2, o, us, uis, dt);
 }
 
 void group_destroy(hs_ctx* g);
@@ -598,6 +689,22 @@ int create_single(const hs_config& cfg_in, hs_ctx** out) {
     c->fimg = c->fpitch * c->frows;
 
     auto bail = [&](int code) { g_create_err = c->err; destroy_impl(c); return code; };
+    // precision / frame depth (hornSchunck.cpp:23-24 accepts any depth)
+    static const int frame_bytes[7] = {1, 1, 2, 2, 4, 4, 8};
+    if (cfg.frame_dtype < 0 || cfg.frame_dtype > HS_FRAME_F64) return bail(fail(c, HS_ERR_INVALID_ARG, "unknown frame_dtype %d", cfg.frame_dtype));
+    if (cfg.precision != HS_PREC_F32 && cfg.precision != HS_PREC_F64) return bail(fail(c, HS_ERR_INVALID_ARG, "unknown precision %d", cfg.precision));
+    if (cfg.precision == HS_PREC_F32 && cfg.frame_dtype != HS_FRAME_U8)
+        return bail(fail(c, HS_ERR_UNSUPPORTED, "the fp32 path packs exact 8-bit gradients: frames of another depth need "
+                                                "hs_config.precision = HS_PREC_F64 (the reference's own fp64 arithmetic)"));
+    c->f64 = cfg.precision == HS_PREC_F64;
+    c->fdt = cfg.frame_dtype;
+    c->fes = frame_bytes[cfg.frame_dtype];
+    if (c->f64) {
+        if (c->top_seam || c->bot_seam || c->textbook || c->oy0 != 0 || c->oy1 != c->H)
+            return bail(fail(c, HS_ERR_UNSUPPORTED, "HS_PREC_F64 contexts are whole-image, reference-arithmetic contexts"));
+        c->fpitch = (size_t)round_up(c->W * c->fes, 128);
+        c->fimg = c->fpitch * c->frows;
+    }
     if (c->textbook && c->w != 3)
         return bail(fail(c, HS_ERR_INVALID_ARG, "HS_FLAG_TEXTBOOK is a 3x3 weighted average: window_size must be 3"));
     if (c->oy0 < 0 || c->oy1 > c->H || c->oy0 >= c->oy1)
@@ -633,6 +740,15 @@ int create_single(const hs_config& cfg_in, hs_ctx** out) {
     const size_t npx = (size_t)c->plane * c->B;
     HS_CREATE_CUDA(cudaMalloc(&c->d_prev, c->fimg * c->B));
     HS_CREATE_CUDA(cudaMalloc(&c->d_next, c->fimg * c->B));
+    if (c->f64) {   // gx, gy, gt, den, u0, v0, u1, v1 in fp64: one allocation (arena), no fused kernel
+        c->arena_bytes = npx * 8 * sizeof(double);
+        HS_CREATE_CUDA(cudaMalloc(&c->arena, c->arena_bytes));
+        for (int i = 0; i < 8; ++i) c->d64[i] = static_cast<double*>(c->arena) + (size_t)i * npx;
+        c->k = 1; c->kernel_id = 2; c->multi_phase = false;
+        c->timing.temporal_k = 1; c->timing.kernel_id = 2;
+        *out = c;
+        return HS_OK;
+    }
     {   // the four flow planes and the seam inbox share ONE allocation: a single memset zeroes the state
         // (:49-50), and a single IPC handle exposes everything a neighbouring slab writes to
         const size_t pbytes = (npx * sizeof(float2) + 255) / 256 * 256;
@@ -641,7 +757,7 @@ int create_single(const hs_config& cfg_in, hs_ctx** out) {
         c->arena_bytes = c->inbox_off + (ibytes + 255) / 256 * 256;
         HS_CREATE_CUDA(cudaMalloc(&c->arena, c->arena_bytes));
         char* base = static_cast<char*>(c->arena);
-        for (int i = 0; i < 2; ++i) {
+        for (int i = 0; i < 2 && !c->f64; ++i) {
             c->plane_off[i] = (size_t)i * pbytes;
             c->d_uv[i] = reinterpret_cast<float2*>(base + c->plane_off[i]);
         }
@@ -768,6 +884,9 @@ extern "C" {
 
 void hs_destroy(hs_ctx* ctx) { destroy_impl(ctx); }
 
+#define HS_NO_F64(c, name)                                                                                \
+    if ((c)->f64) return fail((c), HS_ERR_UNSUPPORTED, name " is not available on an HS_PREC_F64 context")
+
 #define HS_NO_GROUP(c, name)                                                                              \
     if (!(c)->kids.empty())                                                                               \
         return fail((c), HS_ERR_UNSUPPORTED, name " is not available on a multi-device context (use hs_solve, "   \
@@ -803,6 +922,7 @@ int hs_iterate(hs_ctx* c, int iterations) {
 int hs_iterate_rows(hs_ctx* c, int sweeps, int row_begin, int row_end, int flip) {
     if (!c) return HS_ERR_INVALID_ARG;
     HS_NO_GROUP(c, "hs_iterate_rows");
+    HS_NO_F64(c, "hs_iterate_rows");
     if (c->linked) return fail(c, HS_ERR_STATE, "hs_iterate_rows on a connected row slab: hs_iterate exchanges the halos itself");
     if (!c->prepared) return fail(c, HS_ERR_STATE, "hs_iterate_rows before hs_prepare");
     if (c->kernel_id != 1) return fail(c, HS_ERR_UNSUPPORTED, "hs_iterate_rows needs the fused kernel (window 2..5)");
@@ -822,6 +942,7 @@ int hs_iterate_rows(hs_ctx* c, int sweeps, int row_begin, int row_end, int flip)
 int hs_iterate_until(hs_ctx* c, int max_sweeps, double tolerance, int check_every, int* sweeps_done, double* residual) {
     if (!c) return HS_ERR_INVALID_ARG;
     HS_NO_GROUP(c, "hs_iterate_until");
+    HS_NO_F64(c, "hs_iterate_until");
     if (!c->prepared) return fail(c, HS_ERR_STATE, "hs_iterate_until before hs_prepare");
     if (max_sweeps < 0 || check_every < 1 || !(tolerance >= 0)) return fail(c, HS_ERR_INVALID_ARG, "bad early-exit arguments");
     if (c->top_seam || c->bot_seam) return fail(c, HS_ERR_UNSUPPORTED, "hs_iterate_until needs a whole-image context");
@@ -928,6 +1049,7 @@ int hs_solve_bgr(hs_ctx* c, const uint8_t* prev, size_t ps, const uint8_t* next,
                  void* u, size_t us, void* v, size_t vs, int dt) {
     if (!c) return HS_ERR_INVALID_ARG;
     HS_NO_GROUP(c, "hs_solve_bgr");
+    HS_NO_F64(c, "hs_solve_bgr");
     if (c->B != 1 || c->top_seam || c->bot_seam)
         return fail(c, HS_ERR_UNSUPPORTED, "hs_solve_bgr needs a whole-image, batch == 1 context");
     if (!prev || !next) return fail(c, HS_ERR_INVALID_ARG, "null frame pointer");
@@ -980,6 +1102,13 @@ int hs_gradients(hs_ctx* c, const uint8_t* prev, size_t ps, const uint8_t* next,
     int rc;
     if ((rc = do_upload(c, prev, ps, 0, next, ns, 0))) return rc;
     if ((rc = do_prepare(c))) return rc;
+    if (c->f64) {
+        const double* p[3] = {c->d64[0], c->d64[1], c->d64[2]};
+        void* o3[3] = {gx, gy, gt};
+        if ((rc = f64_copy_out(c, p, 3, o3, os, 0, dt))) return rc;
+        HS_CUDA(c, cudaStreamSynchronize(c->stream));
+        return HS_OK;
+    }
     const long long n = c->plane;
     if ((rc = ensure_out(c, (size_t)n * 3 * es))) return rc;
     char* o = static_cast<char*>(c->d_out);
@@ -1006,6 +1135,7 @@ int hs_gradients(hs_ctx* c, const uint8_t* prev, size_t ps, const uint8_t* next,
 int hs_sample_grid(hs_ctx* c, int delta, double* u, double* v, int* ny_out, int* nx_out) {
     if (!c || delta < 1) return HS_ERR_INVALID_ARG;
     HS_NO_GROUP(c, "hs_sample_grid");
+    HS_NO_F64(c, "hs_sample_grid");
     if (c->B != 1) return fail(c, HS_ERR_UNSUPPORTED, "hs_sample_grid needs a batch == 1 context");
     const int rows = c->oy1 - c->oy0;
     const int ny = (rows + delta - 1) / delta, nx = (c->W + delta - 1) / delta;
@@ -1029,6 +1159,7 @@ int hs_sample_grid(hs_ctx* c, int delta, double* u, double* v, int* ny_out, int*
 int hs_get_device_view(hs_ctx* c, hs_device_view* o) {
     if (!c || !o) return HS_ERR_INVALID_ARG;
     HS_NO_GROUP(c, "hs_get_device_view");
+    HS_NO_F64(c, "hs_get_device_view");
     o->prev = c->d_prev; o->next = c->d_next;
     o->frame_pitch = c->fpitch; o->frame_pair_stride = c->fimg;
     o->frame_rows = c->frows; o->frame_row0 = c->frow0;
@@ -1130,6 +1261,7 @@ extern "C" int hs_video_push(hs_ctx* c, const uint8_t* frame, size_t stride, voi
     if (!c || !pair_index) return HS_ERR_INVALID_ARG;
     *pair_index = -1;
     HS_NO_GROUP(c, "hs_video_push");
+    HS_NO_F64(c, "hs_video_push");
     if (!frame) return fail(c, HS_ERR_INVALID_ARG, "null frame pointer");
     if (stride < (size_t)c->W) return fail(c, HS_ERR_INVALID_ARG, "row stride smaller than width");
     DevGuard g(c->dev);

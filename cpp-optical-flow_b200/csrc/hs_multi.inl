@@ -175,6 +175,7 @@ int slab_connect(hs_ctx* c, const HandleBody* up, const HandleBody* dn) {
 }
 
 int create_slab_rank(const hs_config& cfg, hs_ctx** out) {
+    if (cfg.precision != HS_PREC_F32) return fail(nullptr, HS_ERR_UNSUPPORTED, "row slabs run the fp32 fused kernel");
     if (cfg.batch > 1) return fail(nullptr, HS_ERR_UNSUPPORTED, "row slabs need batch == 1");
     if (cfg.window_size < 1 || cfg.width < 1 || cfg.height < 1) return fail(nullptr, HS_ERR_INVALID_ARG, "bad geometry");
     if (cfg.slab_rank < 0 || cfg.slab_rank >= cfg.slab_world) return fail(nullptr, HS_ERR_INVALID_ARG, "slab_rank %d not in [0, %d)", cfg.slab_rank, cfg.slab_world);
@@ -285,6 +286,8 @@ int adopt_error(hs_ctx* g, hs_ctx* kid, int rc) {
 
 int create_group(const hs_config& cfg, hs_ctx** out) {
     const int n = cfg.num_devices;
+    if (cfg.precision != HS_PREC_F32 && cfg.decomposition == HS_DECOMP_ROW_SLAB)
+        return fail(nullptr, HS_ERR_UNSUPPORTED, "row slabs run the fp32 fused kernel (HS_PREC_F64 is a single-device diagnostic path)");
     if (cfg.width < 1 || cfg.height < 1 || cfg.window_size < 1) return fail(nullptr, HS_ERR_INVALID_ARG, "bad geometry");
     if (cfg.decomposition != HS_DECOMP_BATCH && cfg.decomposition != HS_DECOMP_ROW_SLAB)
         return fail(nullptr, HS_ERR_INVALID_ARG, "unknown decomposition %d", cfg.decomposition);

@@ -14,6 +14,12 @@ import numpy as np
 from . import hs_ctypes as H
 
 
+# cv::Mat depths the reference accepts (convertTo(CV_64FC1), hornSchunck.cpp:23-24) -> hs_frame_dtype
+FRAME_DTYPES = {np.dtype(np.uint8): H.FRAME_U8, np.dtype(np.int8): H.FRAME_S8, np.dtype(np.uint16): H.FRAME_U16,
+                np.dtype(np.int16): H.FRAME_S16, np.dtype(np.int32): H.FRAME_S32, np.dtype(np.float32): H.FRAME_F32,
+                np.dtype(np.float64): H.FRAME_F64}
+
+
 def _as_u8_image(img: np.ndarray, name: str) -> np.ndarray:
     a = np.asarray(img)
     if a.ndim != 2:
@@ -36,7 +42,8 @@ class Solver:
 
     def __init__(self, width, height, window_size, max_iterations, alpha, batch=1, device=-1,
                  temporal_k=0, flags=0, out_rows=None, stream=None, global_row0=0,
-                 devices=None, decomposition=H.DECOMP_BATCH, exchange=H.EXCHANGE_PEER, slab=None):
+                 devices=None, decomposition=H.DECOMP_BATCH, exchange=H.EXCHANGE_PEER, slab=None,
+                 precision=H.PREC_F32, frame_dtype=np.uint8):
         """devices: list of CUDA ordinals -> ONE context over several GPUs (hs_config.num_devices),
         `decomposition` H.DECOMP_BATCH or H.DECOMP_ROW_SLAB.  slab=(rank, world): this process holds
         one row slab of a `height`-row image (one process per GPU); see slab_info / slab_connect."""
@@ -57,6 +64,10 @@ class Solver:
             cfg.decomposition, cfg.exchange = int(decomposition), int(exchange)
         if slab is not None:
             cfg.slab_rank, cfg.slab_world = int(slab[0]), int(slab[1])
+        self.frame_dtype = np.dtype(frame_dtype)
+        if self.frame_dtype not in FRAME_DTYPES:
+            raise ValueError(f"unsupported frame dtype {self.frame_dtype}")
+        cfg.precision, cfg.frame_dtype = int(precision), FRAME_DTYPES[self.frame_dtype]
         self._ctx = C.c_void_p()
         rc = self._lib.hs_create(C.byref(cfg), C.byref(self._ctx))
         if rc != H.HS_OK:
@@ -117,13 +128,27 @@ class Solver:
 
     def _frames(self, prev, nxt):
         """-> (prev, next, row strides, image strides) for (H, W) or (B, H, W) uint8 input."""
-        if self.batch == 1 and np.asarray(prev).ndim == 2:
+        if self.frame_dtype != np.uint8:                  # HS_PREC_F64 contexts take frames of their own depth
+            p, n = np.asarray(prev), np.asarray(nxt)
+            if p.dtype != self.frame_dtype or n.dtype != self.frame_dtype:
+                raise ValueError(f"frames are {p.dtype}/{n.dtype}, context was created for {self.frame_dtype}")
+            p = np.ascontiguousarray(p); n = np.ascontiguousarray(n)
+            if self.batch == 1 and p.ndim == 2:
+                shape, ps, ns, pis, nis = p.shape, p.strides[0], n.strides[0], 0, 0
+            else:
+                if p.ndim != 3 or p.shape[0] != self.batch:
+                    raise ValueError(f"expected {self.batch} frames, got shape {p.shape}")
+                shape, ps, ns, pis, nis = p.shape[1:], p.strides[1], n.strides[1], p.strides[0], n.strides[0]
+        elif self.batch == 1 and np.asarray(prev).ndim == 2:
             p, n = _as_u8_image(prev, "prev"), _as_u8_image(nxt, "next")
             shape = p.shape
             ps, ns, pis, nis = p.strides[0], n.strides[0], 0, 0
         else:
-            p = np.ascontiguousarray(prev, dtype=np.uint8)
-            n = np.ascontiguousarray(nxt, dtype=np.uint8)
+            p, n = np.asarray(prev), np.asarray(nxt)
+            if p.ndim == 3:                               # the same lossless rule as for single frames
+                p = np.stack([_as_u8_image(f, "prev") for f in p]); n = np.stack([_as_u8_image(f, "next") for f in n])
+            p = np.ascontiguousarray(p, dtype=np.uint8)
+            n = np.ascontiguousarray(n, dtype=np.uint8)
             if p.ndim != 3 or p.shape[0] != self.batch:
                 raise ValueError(f"expected {self.batch} frames, got shape {p.shape}")
             shape = p.shape[1:]
@@ -280,31 +305,55 @@ class hornSchunck:  # noqa: N801 - the reference's class name (hornSchunck.cpp:8
     (main.cpp:97-98).  C++ out-parameters become return values; outputs are float64 H x W arrays,
     freshly allocated, like the CV_64FC1 Mats of the reference."""
 
-    def __init__(self, inpWindowSize, inpMaxIterations, inpAlpha, device=-1):
+    def __init__(self, inpWindowSize, inpMaxIterations, inpAlpha, device=-1, precision="f32"):
+        """precision: "f32" = the fast fused path (8-bit frames, within 1e-4 px of the reference);
+        "f64" = the reference's own fp64 arithmetic, bit-identical to the fp64 oracle.  Frames that do
+        not hold 8-bit integers (the reference takes any depth, :23-24) always use "f64"."""
         self.windowSize = int(inpWindowSize)        # :14
         self.maxIterations = int(inpMaxIterations)  # :15
         self.alpha = float(inpAlpha)                # :16
+        self.precision = precision
         self._device = device
         self._solver = None
         self._key = None
 
-    def _ctx_for(self, shape):
-        key = (shape, self.windowSize, self.maxIterations, self.alpha)
+    def _ctx_for(self, shape, frame_dtype=np.uint8, f64=False):
+        key = (shape, self.windowSize, self.maxIterations, self.alpha, np.dtype(frame_dtype), f64)
         if key != self._key:
             if self._solver is not None:
                 self._solver.close()
             self._solver = Solver(shape[1], shape[0], self.windowSize, self.maxIterations, self.alpha,
-                                  device=self._device)
+                                  device=self._device, precision=H.PREC_F64 if f64 else H.PREC_F32,
+                                  frame_dtype=frame_dtype)
             self._key = key
         return self._solver
 
+    def _route(self, imagePrev, imageNext):         # noqa: N803
+        """-> (solver, prev, next): 8-bit frames on the fp32 path unless "f64" was asked for; anything
+        else on the fp64 path in its own depth."""
+        p, n = np.asarray(imagePrev), np.asarray(imageNext)
+        if p.ndim != 2 or n.ndim != 2:
+            raise ValueError("expected single-channel 2-D images (convert colour frames first, main.cpp:11-26)")
+        if p.shape != n.shape:
+            raise ValueError("Image sizes are different. Please provide images of same size.")  # main.cpp:70-73
+        if self.precision != "f64":
+            try:
+                p8, n8 = _as_u8_image(p, "imagePrev"), _as_u8_image(n, "imageNext")
+                return self._ctx_for(p8.shape), p8, n8
+            except ValueError:
+                pass                                  # not 8-bit integers: the reference's fp64 path
+        if p.dtype != n.dtype or p.dtype not in FRAME_DTYPES:
+            dt = np.float64 if (p.dtype.kind == "f" or n.dtype.kind == "f" or p.dtype.itemsize > 4) else np.int32
+            p, n = p.astype(dt), n.astype(dt)
+        return self._ctx_for(p.shape, p.dtype, True), p, n
+
     def getGradients(self, imagePrev, imageNext):   # noqa: N802,N803
-        p = _as_u8_image(imagePrev, "imagePrev")
-        return self._ctx_for(p.shape).gradients(p, imageNext, np.float64)
+        s, p, n = self._route(imagePrev, imageNext)
+        return s.gradients(p, n, np.float64)
 
     def getFlow(self, imagePrev, imageNext):        # noqa: N802,N803
-        p = _as_u8_image(imagePrev, "imagePrev")
-        return self._ctx_for(p.shape).solve(p, imageNext, np.float64)
+        s, p, n = self._route(imagePrev, imageNext)
+        return s.solve(p, n, np.float64)
 
     def close(self):
         if self._solver is not None:

@@ -413,6 +413,27 @@ def test_row_slab_group_in_kernel_exchange_equals_single_solve(pkg, w, k, nslab,
     assert np.array_equal(u2, gu2) and np.array_equal(v2, gv2)
 
 
+def _build_c(tmp_path, name):
+    import subprocess
+    from conftest import ROOT
+    libdir = os.path.join(ROOT, "cpp-optical-flow_b200")
+    exe = str(tmp_path / name)
+    subprocess.run(["/usr/bin/gcc", "-std=c99", "-O1", "-Wall", "-Wextra", "-Werror", "-pedantic", "-I", os.path.join(ROOT, "include"),
+                    os.path.join(ROOT, "tests", "c", name + ".c"), "-o", exe, "-L", libdir, "-l:libhs_b200.so",
+                    f"-Wl,-rpath,{libdir}"], check=True)
+    return exe
+
+
+@pytest.mark.parametrize("n", [2, 3, 4])
+def test_plain_c_caller_drives_row_slabs_through_the_abi(pkg, tmp_path, n):
+    """tests/c/slab_smoke.c: hs_config.num_devices / device_ids / decomposition from pedantic C99; the n slabs
+    share device 0 here (on a multi-GPU box run it with `distinct`, tools/gpu_multi.sh does)."""
+    import subprocess
+    pkg.load_library()
+    r = subprocess.run([_build_c(tmp_path, "slab_smoke"), str(n), "same"], capture_output=True, text=True)
+    assert r.returncode == 0 and "bit-identical" in r.stdout, (r.returncode, r.stdout, r.stderr)
+
+
 def test_slab_rank_contexts_plan_export_and_connect(pkg):
     """One process per GPU API (slab_world / slab_rank + hs_slab_export / hs_slab_connect): plan, handles and
     wiring.  (Running two connected slabs as separate launches on ONE GPU is not allowed - kernels that wait
@@ -573,6 +594,78 @@ def test_config3_4k_2000_sweeps_vs_fp64_oracle(pkg, c_oracle, record):
     du, dv, epe = deltas(u, v, ou, ov)
     record(case="4k w=3 T=2000", k=k, max_du=du, max_dv=dv, epe=epe, umax=float(np.abs(ou).max()))
     assert du <= TOL_MAX and dv <= TOL_MAX and epe <= TOL_EPE, f"max|du|={du:.3e} max|dv|={dv:.3e} mean EPE diff={epe:.3e}"
+
+
+# ---------------------------------------------------------------- HS_PREC_F64: the reference's arithmetic, bit for bit
+@pytest.mark.parametrize("w,iters,shape", [(3, 100, (97, 150)), (5, 100, (120, 161)), (1, 7, (33, 47)), (2, 9, (64, 96)),
+                                           (4, 9, (37, 131)), (7, 30, (64, 80)), (9, 5, (40, 64)), (3, 1, (1, 1)), (5, 3, (1, 7))])
+def test_f64_path_is_bit_identical_to_the_fp64_oracle(pkg, c_oracle, oracle, w, iters, shape):
+    """precision = HS_PREC_F64 repeats hornSchunck.cpp:19-75 operation by operation in fp64: gradients AND flow
+    equal the oracle's bits (C oracle for any w; cv2's own filter2D / Sobel for w <= 7)."""
+    from cpp_optical_flow_b200 import hs_ctypes as H
+    a, b = rand_pair(shape, seed=w * 13 + iters)
+    ou, ov = c_oracle.flow(a, b, w, iters, 0.7)
+    with pkg.Solver(shape[1], shape[0], w, iters, 0.7, precision=H.PREC_F64) as s:
+        gx, gy, gt = s.gradients(a, b)
+        u, v = s.solve(a, b, np.float64)
+        u32, v32 = s.solve(a, b, np.float32)
+        assert s.timing().kernel_id == 2
+    assert np.array_equal(u, ou) and np.array_equal(v, ov)
+    assert np.array_equal(u32, ou.astype(np.float32)) and np.array_equal(v32, ov.astype(np.float32))
+    og = oracle.np_gradients(a, b)
+    assert all(np.array_equal(x, y) for x, y in zip((gx, gy, gt), og))
+    if w <= 7 and min(shape) >= 2:
+        *_, cu, cv_ = oracle.cv_flow(a, b, w, iters, 0.7)
+        assert np.array_equal(u, cu) and np.array_equal(v, cv_)
+
+
+def test_f64_path_separates_fp32_rounding_from_kernel_bugs(pkg, c_oracle, kitti, record):
+    """The A/B the fp32 worst case calls for: KITTI 000050, w=3, 1000 sweeps.  fp64 path == oracle
+    bit for bit, so the whole 4e-5 of the fp32 path is rounding."""
+    from cpp_optical_flow_b200 import hs_ctypes as H
+    a, b = kitti("000050")
+    ou, ov = c_oracle.flow(a, b, 3, 1000, 1.0)
+    with pkg.Solver(a.shape[1], a.shape[0], 3, 1000, 1.0, precision=H.PREC_F64) as s:
+        u, v = s.solve(a, b, np.float64)
+        ms = s.timing().iterate_ms
+    assert np.array_equal(u, ou) and np.array_equal(v, ov)
+    record(case="kitti 000050 w=3 T=1000 HS_PREC_F64", max_du=0.0, max_dv=0.0, epe=0.0, iterate_ms=ms,
+           gpixit_s=a.size * 1000 / ms / 1e6)
+
+
+@pytest.mark.parametrize("dtype,scale", [(np.float32, 1.0 / 255), (np.float64, 1.0 / 255), (np.uint16, 257), (np.int16, -3),
+                                         (np.int32, 1000), (np.int8, None)])
+def test_frames_of_any_depth_like_the_reference(pkg, c_oracle, oracle, dtype, scale):
+    """hornSchunck.cpp:23-24 converts frames of ANY depth to CV_64FC1.  CV_32F frames in [0,1], 16-bit frames,
+    negative values: the mirror class routes them to the fp64 path; result == oracle on the same values."""
+    a8, b8 = rand_pair((90, 140), seed=5)
+    if scale is None:
+        a, b = (a8.astype(np.int16) - 128).astype(np.int8), (b8.astype(np.int16) - 128).astype(np.int8)
+    else:
+        a, b = (a8.astype(np.float64) * scale).astype(dtype), (b8.astype(np.float64) * scale).astype(dtype)
+    assert a.dtype == dtype
+    ou, ov = c_oracle.flow_real(a.astype(np.float64), b.astype(np.float64), 3, 40, 0.5)
+    hs = pkg.hornSchunck(3, 40, 0.5)
+    u, v = hs.getFlow(a, b)
+    gx, gy, gt = hs.getGradients(a, b)
+    hs.close()
+    assert np.array_equal(u, ou) and np.array_equal(v, ov)
+    ogx, ogy, ogt = oracle.np_gradients(a.astype(np.float64), b.astype(np.float64))
+    assert np.array_equal(gx, ogx) and np.array_equal(gy, ogy) and np.array_equal(gt, ogt)
+    *_, cu, cv_ = oracle.cv_flow(a, b, 3, 40, 0.5)        # OpenCV's own Sobel sums floats in another order
+    assert np.abs(u - cu).max() <= 1e-9 * max(1.0, np.abs(cu).max()) and np.abs(v - cv_).max() <= 1e-9 * max(1.0, np.abs(cv_).max())
+
+
+def test_fp32_path_refuses_frames_it_cannot_represent(pkg):
+    from cpp_optical_flow_b200 import hs_ctypes as H
+    with pytest.raises(H.HsError) as e:
+        pkg.Solver(32, 32, 3, 5, 1.0, frame_dtype=np.float32)             # fp32 path + float frames
+    assert e.value.status == 4 and "HS_PREC_F64" in str(e.value)
+    with pkg.Solver(32, 32, 3, 5, 1.0, precision=H.PREC_F64, frame_dtype=np.float32) as s:
+        with pytest.raises(ValueError):
+            s.solve(np.zeros((32, 32), np.uint8), np.zeros((32, 32), np.uint8))
+        with pytest.raises(H.HsError):
+            s.iterate_rows(1, 0, 4, True)
 
 
 # ---------------------------------------------------------------- error behaviour
