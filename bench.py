@@ -141,7 +141,7 @@ class ClockSampler:
 REF_BINARY = os.path.join(ROOT, "oracle", "_ref", "hs_ref")   # built by `make -C oracle ref` iff OpenCV C++ exists
 
 
-def reference_solve_seconds(prev, nxt, window, iters, alpha):
+def reference_solve_seconds(prev, nxt, window, iters, alpha, threads=0):
     """Wall seconds of ONE getFlow of the reference's CPU path on these frames, and what ran:
     ("reference", threads, description) when the unmodified hornSchunck.cpp could be compiled here
     (oracle/_ref/hs_ref), else ("port", ...) = the line-by-line cv2 restatement."""
@@ -157,6 +157,7 @@ def reference_solve_seconds(prev, nxt, window, iters, alpha):
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import cv2
     import hs_oracle
+    cv2.setNumThreads(int(threads) if threads else -1)        # 1 = the single-threaded reference of configs[0]; -1 = default
     t0 = time.perf_counter()
     hs_oracle.cv_flow(prev, nxt, window, iters, alpha)
     return (time.perf_counter() - t0, "port", cv2.getNumThreads(),
@@ -164,14 +165,14 @@ def reference_solve_seconds(prev, nxt, window, iters, alpha):
             "(C++ OpenCV absent: hornSchunck.cpp not compilable here)")
 
 
-def cpu_reference_rate(prev, nxt, window, alpha, seconds_budget):
+def cpu_reference_rate(prev, nxt, window, alpha, seconds_budget, threads=0):
     """Time the reference's CPU path on a bounded number of sweeps of this workload."""
-    t2, kind, threads, what = reference_solve_seconds(prev, nxt, window, 2, alpha)   # incl. the gradient stage
+    t2, kind, nthr, what = reference_solve_seconds(prev, nxt, window, 2, alpha, threads)   # incl. the gradient stage
     per_iter = max(t2 / 2.0, 1e-4)
     iters = int(min(max(seconds_budget / per_iter, 4), 400))
-    dt, kind, threads, what = reference_solve_seconds(prev, nxt, window, iters, alpha)
+    dt, kind, nthr, what = reference_solve_seconds(prev, nxt, window, iters, alpha, threads)
     rate = prev.shape[0] * prev.shape[1] * iters / dt / 1e6
-    return rate, threads, iters, dt, kind, what
+    return rate, nthr, iters, dt, kind, what
 
 
 def run_reference(args, rank, world):
@@ -318,20 +319,46 @@ def run_ours(args, rank, local_rank, world):
             raise RuntimeError(lib.hs_last_error(solver._ctx))
 
     e2e_steps = max(3, min(args.steps, 10))
-    solve_host()
-    barrier(); torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        with torch.cuda.stream(stream):
-            flush.zero_()
-        stream.synchronize()
-        solve_host()
-    torch.cuda.synchronize()
-    e2e_t = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
-    e2e_value = float(H) * W * T * e2e_steps * world / float(e2e_t.item()) / 1e6
+
+    def time_calls(fn):
+        """Wall time of e2e_steps synchronous calls of `fn` (host buffers in, host buffers out); the L2 flush
+        between steps is outside the timed region.  Max over ranks -> whole-job throughput."""
+        fn()
+        barrier(); torch.cuda.synchronize()
+        tot = 0.0
+        for _ in range(e2e_steps):
+            with torch.cuda.stream(stream):
+                flush.zero_()
+            stream.synchronize()
+            t0 = time.perf_counter()
+            fn()
+            tot += time.perf_counter() - t0
+        t = torch.tensor([tot], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(H) * W * T * e2e_steps * world / float(t.item()) / 1e6
+
+    e2e_value = time_calls(solve_host)
     et = solver.timing()
+    # the same call with float32 outputs (half the D2H bytes; what a caller that does not need CV_64FC1 gets)
+    hu32 = torch.empty((H, W), dtype=torch.float32).pin_memory(); hv32 = torch.empty((H, W), dtype=torch.float32).pin_memory()
+
+    def solve_host_f32():
+        rc = lib.hs_solve(solver._ctx, hp.data_ptr(), W, 0, hn.data_ptr(), W, 0, hu32.data_ptr(), W * 4, 0,
+                          hv32.data_ptr(), W * 4, 0, HC.HS_F32)
+        if rc:
+            raise RuntimeError(lib.hs_last_error(solver._ctx))
+    e2e_f32 = time_calls(solve_host_f32)
+    # ... and from PAGEABLE host memory, which is what a cv::Mat hands the adapter unless it registers it
+    pu = np.empty((H, W), np.float64); pv = np.empty((H, W), np.float64)
+    pp, pn = np.array(prev), np.array(nxt)
+
+    def solve_pageable():
+        rc = lib.hs_solve(solver._ctx, pp.ctypes.data, W, 0, pn.ctypes.data, W, 0, pu.ctypes.data, W * 8, 0,
+                          pv.ctypes.data, W * 8, 0, HC.HS_F64)
+        if rc:
+            raise RuntimeError(lib.hs_last_error(solver._ctx))
+    e2e_pageable = time_calls(solve_pageable)
 
     # ---- the same through the streaming front-end (frame sequences: each frame uploaded once,
     #      H2D / solve / D2H of consecutive pairs overlapped) ------------------------------------
@@ -407,9 +434,13 @@ def run_ours(args, rank, local_rank, world):
 
     cpu = None
     if world == 1 and not args.no_cpu and not args.textbook:
-        rate, threads, its, dt, kind, what = cpu_reference_rate(prev, nxt, window, 1.0, args.cpu_seconds)
+        # headline: ONE thread, as BASELINE configs[0] / BASELINE.md 4.3 specify; all host cores beside it
+        rate, threads, its, dt, kind, what = cpu_reference_rate(prev, nxt, window, 1.0, args.cpu_seconds, threads=1)
+        rate_all, threads_all, its_all, dt_all, _, _ = cpu_reference_rate(prev, nxt, window, 1.0, args.cpu_seconds / 2)
         cpu = {"value": rate, "unit": "Mpixel-iter/s", "cores": threads, "kind": kind,
-               "sample": f"same {W}x{H} pair, {its} of {T} sweeps ({dt:.1f} s)", "what": what}
+               "sample": f"same {W}x{H} pair, {its} of {T} sweeps ({dt:.1f} s)", "what": what,
+               "all_cores": {"value": rate_all, "cores": threads_all,
+                             "sample": f"same pair, {its_all} of {T} sweeps ({dt_all:.1f} s)"}}
 
     line = {"metric": METRIC, "value": value, "unit": "Mpixel-iter/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": float(np.mean(step_ms)), "higher_is_better": True,
@@ -422,6 +453,8 @@ def run_ours(args, rank, local_rank, world):
             "roofline": roofline,
             "e2e": {"value": e2e_value, "unit": "Mpixel-iter/s", "h2d_bytes_per_step": 2 * H * W,
                     "d2h_bytes_per_step": 2 * H * W * 8, "steps": e2e_steps,
+                    "note": "hs_solve: pinned host uint8 frames in, pinned float64 u, v out (the reference's CV_64FC1)",
+                    "value_f32_outputs": e2e_f32, "value_pageable_buffers": e2e_pageable,
                     "stream_value": stream_value,
                     "stream_note": "hs_video_push: consecutive pairs of a frame sequence, one frame uploaded per pair, "
                                    "H2D/solve/D2H overlapped (L2 not flushed between pairs)",

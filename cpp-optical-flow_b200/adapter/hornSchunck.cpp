@@ -12,9 +12,12 @@
 //
 // Outputs are freshly allocated, continuous CV_64FC1 H x W Mats (the caller's headers are
 // replaced, like `u = cv::Mat::zeros(...)` / `u = uAvg - uUpdateConst` do upstream); inputs may be
-// non-continuous (ROI views): Mat::step is passed through.  Frames must hold 8-bit integer
-// values; 8UC1 is taken as is (what main.cpp's preprocess() produces), other depths are accepted
-// when every value is an integer in [0,255] (the reference converts any depth to CV_64F, :23-24).
+// non-continuous (ROI views): Mat::step is passed through.  Frames of ANY depth are accepted, as
+// upstream (convertTo(CV_64FC1), :23-24): 8UC1 - what main.cpp's preprocess() produces - and any
+// other depth whose values are all integers in [0,255] run on the fast fp32 path (within 1e-4 px of
+// the reference's fp64 result); everything else (CV_32F in [0,1], 16-bit, negative values ...) runs
+// on the library's HS_PREC_F64 path in its own depth, which repeats the reference's fp64 arithmetic
+// bit for bit.  Set `precision = HS_PREC_F64` to force that path for 8-bit frames too.
 #ifndef HS_B200_HORNSCHUNCK_ADAPTER
 #define HS_B200_HORNSCHUNCK_ADAPTER
 
@@ -33,6 +36,7 @@ class hornSchunck{
 public:
     int windowSize, maxIterations;
     double alpha;
+    int precision = HS_PREC_F32;      // extension (not in the reference): HS_PREC_F64 = fp64 arithmetic for every frame
 
     hornSchunck(int inpWindowSize, int inpMaxIterations, double inpAlpha)
         : windowSize(inpWindowSize), maxIterations(inpMaxIterations), alpha(inpAlpha) {}
@@ -48,8 +52,9 @@ public:
 
     void getGradients(cv::Mat imagePrev, cv::Mat imageNext, cv::Mat &gradX, cv::Mat &gradY, cv::Mat &gradT){
         cv::Mat p8, n8;
-        checkPair(imagePrev, imageNext, p8, n8);
-        hs_ctx* ctx = context(p8.cols, p8.rows);
+        int fdt = HS_FRAME_U8;
+        checkPair(imagePrev, imageNext, p8, n8, fdt);
+        hs_ctx* ctx = context(p8.cols, p8.rows, fdt);
         cv::Mat gx(p8.rows, p8.cols, CV_64FC1), gy(p8.rows, p8.cols, CV_64FC1), gt(p8.rows, p8.cols, CV_64FC1);
         check(hs_gradients(ctx, p8.data, (size_t)p8.step, n8.data, (size_t)n8.step,
                            gx.data, gy.data, gt.data, (size_t)gx.step, HS_F64), ctx);
@@ -58,8 +63,9 @@ public:
 
     void getFlow(cv::Mat imagePrev, cv::Mat imageNext, cv::Mat &u, cv::Mat &v){
         cv::Mat p8, n8;
-        checkPair(imagePrev, imageNext, p8, n8);
-        hs_ctx* ctx = context(p8.cols, p8.rows);
+        int fdt = HS_FRAME_U8;
+        checkPair(imagePrev, imageNext, p8, n8, fdt);
+        hs_ctx* ctx = context(p8.cols, p8.rows, fdt);
         cv::Mat uu(p8.rows, p8.cols, CV_64FC1), vv(p8.rows, p8.cols, CV_64FC1);
         check(hs_solve(ctx, p8.data, (size_t)p8.step, 0, n8.data, (size_t)n8.step, 0,
                        uu.data, (size_t)uu.step, 0, vv.data, (size_t)vv.step, 0, HS_F64), ctx);
@@ -68,7 +74,7 @@ public:
 
 private:
     hs_ctx* ctx_ = nullptr;
-    int cw_ = 0, ch_ = 0, cwin_ = 0, cit_ = 0;
+    int cw_ = 0, ch_ = 0, cwin_ = 0, cit_ = 0, cfdt_ = 0, cprec_ = 0;
     double calpha_ = 0;
 
     void release() { if (ctx_) { hs_destroy(ctx_); ctx_ = nullptr; } }
@@ -82,8 +88,10 @@ private:
     }
 
     // one context per (geometry, parameters); the public fields may be changed between calls
-    hs_ctx* context(int width, int height) {
-        if (ctx_ && cw_ == width && ch_ == height && cwin_ == windowSize && cit_ == maxIterations && calpha_ == alpha)
+    hs_ctx* context(int width, int height, int fdt) {
+        const int prec = (fdt != HS_FRAME_U8 || precision == HS_PREC_F64) ? HS_PREC_F64 : HS_PREC_F32;
+        if (ctx_ && cw_ == width && ch_ == height && cwin_ == windowSize && cit_ == maxIterations && calpha_ == alpha &&
+            cfdt_ == fdt && cprec_ == prec)
             return ctx_;
         release();
         hs_config cfg = {};
@@ -91,49 +99,66 @@ private:
         cfg.width = width; cfg.height = height;
         cfg.window_size = windowSize; cfg.max_iterations = maxIterations; cfg.alpha = alpha;
         cfg.batch = 1; cfg.device = -1;
+        cfg.precision = prec; cfg.frame_dtype = fdt;
         hs_ctx* c = nullptr;
         check(hs_create(&cfg, &c), nullptr);
         ctx_ = c; cw_ = width; ch_ = height; cwin_ = windowSize; cit_ = maxIterations; calpha_ = alpha;
+        cfdt_ = fdt; cprec_ = prec;
         return ctx_;
     }
 
+    // lossless narrowing to 8-bit; false when some value is not an integer in [0, 255]
     template <typename T>
-    static void narrow(const cv::Mat& src, cv::Mat& dst) {
+    static bool narrow(const cv::Mat& src, cv::Mat& dst) {
         dst = cv::Mat(src.rows, src.cols, CV_8UC1);
         for (int y = 0; y < src.rows; ++y) {
             const T* s = src.ptr<T>(y);
             unsigned char* d = dst.ptr<unsigned char>(y);
             for (int x = 0; x < src.cols; ++x) {
                 const T val = s[x];
-                if (!(val >= (T)0 && val <= (T)255) || (T)(unsigned char)val != val)
-                    CV_Error(cv::Error::StsUnsupportedFormat,
-                             "hs_b200: frames must hold 8-bit integer values (the device path reads uint8 frames)");
+                if (!(val >= (T)0 && val <= (T)255) || (T)(unsigned char)val != val) return false;
                 d[x] = (unsigned char)val;
             }
         }
+        return true;
     }
 
-    static void to8u(const cv::Mat& src, cv::Mat& dst) {
+    static bool to8u(const cv::Mat& src, cv::Mat& dst) {
         switch (src.depth()) {
-            case CV_8U:  dst = src; break;                       // shared header, no copy
-            case CV_8S:  narrow<signed char>(src, dst); break;
-            case CV_16U: narrow<unsigned short>(src, dst); break;
-            case CV_16S: narrow<short>(src, dst); break;
-            case CV_32S: narrow<int>(src, dst); break;
-            case CV_32F: narrow<float>(src, dst); break;
-            case CV_64F: narrow<double>(src, dst); break;
+            case CV_8U:  dst = src; return true;                 // shared header, no copy
+            case CV_8S:  return narrow<signed char>(src, dst);
+            case CV_16U: return narrow<unsigned short>(src, dst);
+            case CV_16S: return narrow<short>(src, dst);
+            case CV_32S: return narrow<int>(src, dst);
+            case CV_32F: return narrow<float>(src, dst);
+            case CV_64F: return narrow<double>(src, dst);
             default: CV_Error(cv::Error::StsUnsupportedFormat, "hs_b200: unsupported frame depth");
         }
+        return false;
     }
 
-    static void checkPair(const cv::Mat& a, const cv::Mat& b, cv::Mat& a8, cv::Mat& b8) {
+    static int frameDtype(int depth) {
+        switch (depth) {
+            case CV_8U: return HS_FRAME_U8;   case CV_8S: return HS_FRAME_S8;
+            case CV_16U: return HS_FRAME_U16; case CV_16S: return HS_FRAME_S16;
+            case CV_32S: return HS_FRAME_S32; case CV_32F: return HS_FRAME_F32;
+            case CV_64F: return HS_FRAME_F64;
+            default: CV_Error(cv::Error::StsUnsupportedFormat, "hs_b200: unsupported frame depth");
+        }
+        return HS_FRAME_U8;
+    }
+
+    // a, b -> the frames the library gets (shared headers where possible) and their hs_frame_dtype
+    static void checkPair(const cv::Mat& a, const cv::Mat& b, cv::Mat& fa, cv::Mat& fb, int& fdt) {
         if (a.empty() || b.empty()) CV_Error(cv::Error::StsBadArg, "hs_b200: empty frame");
         if (a.channels() != 1 || b.channels() != 1)
             CV_Error(cv::Error::StsBadArg, "hs_b200: frames must be single-channel (see preprocess(), main.cpp:11-26)");
         if (a.rows != b.rows || a.cols != b.cols)
             CV_Error(cv::Error::StsUnmatchedSizes, "hs_b200: Image sizes are different (main.cpp:70-73)");
-        to8u(a, a8);
-        to8u(b, b8);
+        if (to8u(a, fa) && to8u(b, fb)) { fdt = HS_FRAME_U8; return; }
+        if (a.depth() != b.depth()) CV_Error(cv::Error::StsUnmatchedFormats, "hs_b200: the two frames must have the same depth");
+        fa = a; fb = b;                                          // any other depth: fp64 path, frames as they are
+        fdt = frameDtype(a.depth());
     }
 };
 

@@ -184,6 +184,59 @@ int env_int(const char* name, int dflt) {
     return (s && *s) ? atoi(s) : dflt;
 }
 
+// Temporal-blocking depth k (sweeps fused per phase) of the fused kernel: pure host arithmetic, exported
+// as hs_default_temporal_k so that the choice can be checked against the measured sweeps in profiles/.
+//   `asked` > 0: the caller's k, only clamped to what a 128 x 48 staged tile can hold.
+//   Large frames: measured on B200 (profiles/*k_sweep*, profiles/*traffic_table*): radius-1 windows want
+//   k=6 when the planes stream from HBM (fewer bytes per sweep) but k=4 when the 24 B/pixel working set sits
+//   in L2 (better valid fraction per staged tile); radius-2 windows k=3; radius 3..4 (w = 6..9) k=2.
+//   Small and medium frames (less than four tiles per SM) choose k from a cost model of a phase
+//   (microseconds, fitted on B200: profiles/r01j_k_sweep_kitti.jsonl, r01j_k_sweep_mid.jsonl):
+//     a tile costs          item(k)  = k * t_sweep + t_tile
+//     chained launches      phase(k) = ceil(tiles / #SMs) * item + t_launch     (tiles < 1.25 #SMs)
+//     one dataflow launch   phase(k) = max(tiles / #SMs * item, item + t_dep)
+//   and the k with the lowest phase(k) / k wins.  t_dep is the publish -> poll -> TMA chain from a finished
+//   tile to its dependants: with few tiles per SM it, not the arithmetic, paces a phase, and fusing more
+//   sweeps per phase amortises it.
+int choose_temporal_k(int asked, int W, int rows, int row_parity, int B, int RL, int RR, int max_iterations, int num_sms,
+                      bool may_dataflow, bool seam, double plane_px) {
+    const int SY = TILE_R * TILE_NWARP, SX = 128;
+    const int kmax = (SY - 3) / std::max(1, RL + RR);
+    const int rad = std::max(RL, RR);
+    auto tiles = [&](int k) -> size_t {
+        const int vx = SX - round_up(RL * k, 4) - round_up(RR * k, 4);
+        const int hyt = RL * k + ((row_parity + RL * k) & 1);
+        const int vy = (SY - hyt - RR * k) & ~1;
+        if (vx <= 0 || vy <= 0) return 0;
+        return (size_t)((W + vx - 1) / vx) * ((rows + vy - 1) / vy) * B;
+    };
+    int k = asked;
+    if (k <= 0) {
+        const bool l2_resident = plane_px * 24.0 <= 64.0e6;
+        k = rad <= 1 ? (l2_resident ? 4 : 6) : (rad == 2 ? 3 : 2);
+    }
+    k = std::min(k, kmax);
+    // keep a useful centre: at least a quarter of the staged rows must be output rows
+    while (k > 1 && SY - (RL + RR) * k < SY / 4) --k;
+    if (asked <= 0 && !seam && tiles(k) < (size_t)4 * num_sms) {
+        const double t_sweep = rad <= 1 ? 0.59 : 0.97, t_tile = 1.5, t_launch = 2.4, t_dep = 7.5;
+        int kcap = std::min(kmax, rad <= 1 ? 12 : 5);
+        if (max_iterations > 0) kcap = std::min(kcap, max_iterations);
+        double best = 1e300;
+        for (int kk = 1; kk <= kcap; ++kk) {
+            if (kk > 1 && SY - (RL + RR) * kk < SY / 4) break;
+            const size_t n = tiles(kk);
+            if (n == 0) break;
+            const double item = kk * t_sweep + t_tile;
+            const bool dataflow = may_dataflow && n * 4 >= (size_t)num_sms * 5;
+            const double phase = dataflow ? std::max((double)n / num_sms * item, item + t_dep)
+                                          : (double)((n + num_sms - 1) / num_sms) * item + t_launch;
+            if (phase / kk < best) { best = phase / kk; k = kk; }
+        }
+    }
+    return k;
+}
+
 constexpr int EMU_MAXS = 4;     // row slabs of ONE device that a single (emulation) launch can hold
 
 // tile-row geometry of `rows` produced rows whose first row has image-row parity `parity`
@@ -628,6 +681,20 @@ extern "C" {
 
 int hs_version(void) { return HS_VERSION; }
 
+int hs_default_temporal_k(const hs_config* cfg_in, int32_t num_sms) {
+    if (!cfg_in || cfg_in->struct_size == 0 || cfg_in->struct_size > sizeof(hs_config) || num_sms < 1) return 0;
+    hs_config cfg{};
+    memcpy(&cfg, cfg_in, cfg_in->struct_size);
+    if (cfg.width < 1 || cfg.height < 1 || cfg.window_size < 2 || cfg.window_size > 9) return 0;   // 0: no fused kernel
+    const int a = cfg.window_size - cfg.window_size / 2 - 1, RL = a, RR = cfg.window_size - 1 - a;
+    const int B = cfg.batch > 0 ? cfg.batch : 1;
+    const bool seam = cfg.flags & (HS_FLAG_TOP_IS_SEAM | HS_FLAG_BOTTOM_IS_SEAM);
+    int r0 = cfg.out_row_begin, r1 = cfg.out_row_end;
+    if (r0 == 0 && r1 == 0) r1 = cfg.height;
+    return choose_temporal_k(cfg.temporal_k, cfg.width, r1 - r0, r0 + cfg.global_row0, B, RL, RR, cfg.max_iterations, num_sms,
+                             !(cfg.flags & HS_FLAG_SINGLE_PHASE), seam, (double)round_up(cfg.width, 32) * cfg.height * B);
+}
+
 const char* hs_last_error(const hs_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_err.c_str(); }
 
 int hs_create(const hs_config* cfg_in, hs_ctx** out) {
@@ -781,53 +848,11 @@ int create_single(const hs_config& cfg_in, hs_ctx** out) {
         return bail(fail(c, HS_ERR_CUDA, "cudaFuncSetAttribute(max dynamic smem): %s", cudaGetErrorString(e)));
     if (have_tile) {
         using TS0 = hs::TileShape<1, 1, TILE_R, TILE_NWARP>;
-        int k = cfg.temporal_k > 0 ? cfg.temporal_k : env_int("HS_K", 0);
-        if (k <= 0) {
-            // measured on B200 (profiles/*k_sweep*): radius-1 windows want k=6 when the planes stream
-            // from HBM (fewer bytes per sweep) but k=4 when the 24 B/pixel working set sits in L2
-            // (better valid fraction per staged tile); radius-2 windows k=3
-            const bool l2_resident = (double)c->plane * c->B * 24.0 <= 64.0e6;
-            // radius >= 3 (w = 6..9): the halo eats the 48-row stage quickly, k=2
-            const int rad = std::max(c->RL, c->RR);
-            k = rad <= 1 ? (l2_resident ? 4 : 6) : (rad == 2 ? 3 : 2);
-        }
-        k = std::min(k, kmax);
-        // keep a useful centre: at least a quarter of the staged rows must be output rows
-        while (k > 1 && TS0::SY - (c->RL + c->RR) * k < TS0::SY / 4) --k;
-        // Small and medium frames (less than four tiles per SM) choose k from a cost model of a phase
-        // (microseconds, fitted on B200: profiles/r01j_k_sweep_kitti.jsonl, r01j_k_sweep_mid.jsonl):
-        //   a tile costs          item(k)  = k * t_sweep + t_tile
-        //   chained launches      phase(k) = ceil(tiles / #SMs) * item + t_launch     (tiles < 1.25 #SMs)
-        //   one dataflow launch   phase(k) = max(tiles / #SMs * item, item + t_dep)
-        // and the k with the lowest phase(k) / k wins.  t_dep is the publish -> poll -> fence -> TMA
-        // chain from a finished tile to its dependants: with few tiles per SM it, not the arithmetic,
-        // paces a phase, and fusing more sweeps per phase amortises it.  What matters in this regime
-        // is launches, whole waves and that chain, not the valid fraction of a staged tile.  The k
-        // range is the one the parity tests cover.  Larger frames keep the measured defaults above.
-        const bool auto_k = cfg.temporal_k <= 0 && env_int("HS_K", 0) <= 0;
-        if (auto_k && !c->top_seam && !c->bot_seam) {
-            size_t n0 = 0;
-            tile_dispatch(c, [&](auto t) { n0 = decltype(t)::tiles_for(c, k); });
-            if (n0 < (size_t)4 * c->num_sms) {
-                const int rad = std::max(c->RL, c->RR);
-                const double t_sweep = rad <= 1 ? 0.59 : 0.97, t_tile = 1.5, t_launch = 2.4, t_dep = 7.5;
-                int kcap = std::min(kmax, rad <= 1 ? 12 : 5);
-                if (cfg.max_iterations > 0) kcap = std::min(kcap, cfg.max_iterations);
-                const bool may_dataflow = !(cfg.flags & HS_FLAG_SINGLE_PHASE) && env_int("HS_SINGLE_PHASE", 0) == 0;
-                double best = 1e300;
-                for (int kk = 1; kk <= kcap; ++kk) {
-                    if (kk > 1 && TS0::SY - (c->RL + c->RR) * kk < TS0::SY / 4) break;
-                    size_t n = 0;
-                    tile_dispatch(c, [&](auto t) { n = decltype(t)::tiles_for(c, kk); });
-                    if (n == 0) break;
-                    const double item = kk * t_sweep + t_tile;
-                    const bool dataflow = may_dataflow && n * 4 >= (size_t)c->num_sms * 5;
-                    const double phase = dataflow ? std::max((double)n / c->num_sms * item, item + t_dep)
-                                                  : (double)((n + c->num_sms - 1) / c->num_sms) * item + t_launch;
-                    if (phase / kk < best) { best = phase / kk; k = kk; }
-                }
-            }
-        }
+        const bool may_dataflow = !(cfg.flags & HS_FLAG_SINGLE_PHASE) && env_int("HS_SINGLE_PHASE", 0) == 0;
+        const int k = choose_temporal_k(cfg.temporal_k > 0 ? cfg.temporal_k : env_int("HS_K", 0), c->W, c->oy1 - c->oy0,
+                                        c->oy0 + c->grow0, c->B, c->RL, c->RR, cfg.max_iterations, c->num_sms,
+                                        may_dataflow, c->top_seam || c->bot_seam, (double)c->plane * c->B);
+        (void)kmax;
         c->k = k;
         c->kernel_id = 1;
         int rc;

@@ -23,7 +23,7 @@ STATUS_NAMES = {0: "HS_OK", 1: "HS_ERR_INVALID_ARG", 2: "HS_ERR_CUDA", 3: "HS_ER
 SYMBOLS = ["hs_create", "hs_destroy", "hs_solve", "hs_solve_bgr", "hs_gradients", "hs_upload", "hs_prepare",
            "hs_iterate", "hs_iterate_rows", "hs_iterate_until", "hs_solve_device", "hs_download", "hs_sync", "hs_sample_grid", "hs_get_device_view",
            "hs_video_push", "hs_video_flush", "hs_video_reset", "hs_get_timing", "hs_last_error", "hs_version", "hs_host_alloc", "hs_host_free",
-           "hs_get_slab_info", "hs_plan_slab", "hs_slab_export", "hs_slab_connect"]
+           "hs_get_slab_info", "hs_plan_slab", "hs_slab_export", "hs_slab_connect", "hs_default_temporal_k"]
 
 
 class HsConfig(C.Structure):
@@ -111,6 +111,7 @@ def load_library(path: str | None = None):
     lib.hs_version.argtypes = []
     lib.hs_host_alloc.argtypes = [C.POINTER(vp), sz]
     lib.hs_host_free.argtypes = [vp]
+    lib.hs_default_temporal_k.argtypes = [C.POINTER(HsConfig), i32]
     lib.hs_get_slab_info.argtypes = [vp, C.POINTER(HsSlabInfo)]
     lib.hs_plan_slab.argtypes = [i32, i32, i32, i32, i32, C.POINTER(HsSlabInfo)]
     lib.hs_slab_export.argtypes = [vp, C.POINTER(HsSlabHandle)]

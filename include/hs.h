@@ -149,7 +149,7 @@ typedef struct hs_timing {
     float total_ms;
     int32_t launches;   /* kernels launched by the last call              */
     int32_t temporal_k; /* sweeps fused per phase (temporal blocking depth)*/
-    int32_t kernel_id;  /* 0 = generic one-sweep kernel, 1 = fused tile kernel */
+    int32_t kernel_id;  /* 0 = generic one-sweep kernel, 1 = fused tile kernel, 2 = fp64 reference-arithmetic kernel */
 } hs_timing;
 
 /* Device-side view used by device-resident callers (bench, row-slab host code). All pointers
@@ -280,6 +280,10 @@ int hs_slab_connect(hs_ctx* ctx, const hs_slab_handle* up, const hs_slab_handle*
 
 /* ---- introspection --------------------------------------------------------------------------- */
 int hs_get_timing(const hs_ctx* ctx, hs_timing* out);
+/* The temporal-blocking depth hs_create would pick for this configuration on a device with num_sms SMs
+ * (pure host arithmetic, no device needed; 0 = no fused kernel for this window).  The rule is documented in
+ * DESIGN.md section 4 and checked against the measured k sweeps committed under profiles/. */
+int hs_default_temporal_k(const hs_config* cfg, int32_t num_sms);
 const char* hs_last_error(const hs_ctx* ctx); /* ctx may be NULL: last hs_create failure of thread */
 int hs_version(void);
 
