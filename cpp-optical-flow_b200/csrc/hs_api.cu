@@ -191,7 +191,8 @@ int env_int(const char* name, int dflt) {
 //   k=6 when the planes stream from HBM (fewer bytes per sweep) but k=4 when the 24 B/pixel working set sits
 //   in L2 (better valid fraction per staged tile); radius-2 windows k=3; radius 3..4 (w = 6..9) k=2.
 //   Small and medium frames (less than four tiles per SM) choose k from a cost model of a phase
-//   (microseconds, fitted on B200: profiles/r01j_k_sweep_kitti.jsonl, r01j_k_sweep_mid.jsonl):
+//   (microseconds, fitted on B200: profiles/r01j_k_sweep_kitti.jsonl, r01j_k_sweep_mid.jsonl; re-checked against
+//   profiles/r02n_k_sweep.jsonl by tests/test_abi_cpu.py::test_default_k_is_near_the_measured_best):
 //     a tile costs          item(k)  = k * t_sweep + t_tile
 //     chained launches      phase(k) = ceil(tiles / #SMs) * item + t_launch     (tiles < 1.25 #SMs)
 //     one dataflow launch   phase(k) = max(tiles / #SMs * item, item + t_dep)
@@ -219,8 +220,9 @@ int choose_temporal_k(int asked, int W, int rows, int row_parity, int B, int RL,
     // keep a useful centre: at least a quarter of the staged rows must be output rows
     while (k > 1 && SY - (RL + RR) * k < SY / 4) --k;
     if (asked <= 0 && !seam && tiles(k) < (size_t)4 * num_sms) {
-        const double t_sweep = rad <= 1 ? 0.59 : 0.97, t_tile = 1.5, t_launch = 2.4, t_dep = 7.5;
-        int kcap = std::min(kmax, rad <= 1 ? 12 : 5);
+        // (t_dep was 7.5 us while the producer warp paid two MEMBARs per dependency check; 5 us with acquire loads)
+        const double t_sweep = rad <= 1 ? 0.59 : 0.97, t_tile = 1.5, t_launch = 2.4, t_dep = 5.0;
+        int kcap = std::min(kmax, rad <= 1 ? 12 : 6);
         if (max_iterations > 0) kcap = std::min(kcap, max_iterations);
         double best = 1e300;
         for (int kk = 1; kk <= kcap; ++kk) {

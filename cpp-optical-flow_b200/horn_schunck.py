@@ -28,6 +28,9 @@ def _as_u8_image(img: np.ndarray, name: str) -> np.ndarray:
     if a.dtype != np.uint8:
         # the reference converts any depth to CV_64F (:23-24); the device path takes 8-bit frames,
         # so accept other dtypes only when the conversion is lossless
+        # (a range check first: a negative int8 would wrap to uint8 and back unnoticed)
+        if a.size and (a.min() < 0 or a.max() > 255):
+            raise ValueError(f"{name}: dtype {a.dtype} holds values outside [0, 255]")
         b = a.astype(np.uint8)
         if not np.array_equal(b.astype(a.dtype), a):
             raise ValueError(f"{name}: dtype {a.dtype} holds values that are not 8-bit integers")

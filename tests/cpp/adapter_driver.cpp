@@ -2,7 +2,10 @@
 // (HornSchunckOF/main.cpp:93-98) against cpp-optical-flow_b200/adapter/hornSchunck.cpp, compiled
 // with the minicv stub instead of OpenCV.  Reads two raw uint8 frames, writes u, v (float64) and the
 // gradients, so the pytest side can compare with the oracle.
-//   adapter_driver <prev.raw> <next.raw> <rows> <cols> <windowSize> <maxIterations> <alpha> <out.bin> [roi]
+//   adapter_driver <prev.raw> <next.raw> <rows> <cols> <windowSize> <maxIterations> <alpha> <out.bin> [roi|f32|f64prec]
+//     roi     - non-continuous ROI views of the frames
+//     f32     - the frames as CV_32F in [0,1] (value / 255): the reference takes any depth (hornSchunck.cpp:23-24)
+//     f64prec - 8-bit frames, hs.precision = HS_PREC_F64 (the reference's own fp64 arithmetic)
 #include "hornSchunck.cpp"
 #include <cstdio>
 #include <fstream>
@@ -18,9 +21,19 @@ int main(int argc, char** argv) {
     int rows = atoi(argv[3]), cols = atoi(argv[4]);
     std::vector<unsigned char> a = slurp(argv[1]), b = slurp(argv[2]);
     cv::Mat imagePrev(rows, cols, CV_8UC1, a.data()), imageNext(rows, cols, CV_8UC1, b.data());
-    if (argc > 9) {   // exercise non-continuous inputs: drop a 3-pixel border through ROI views
+    const std::string mode = argc > 9 ? argv[9] : "";
+    if (mode == "roi") {   // exercise non-continuous inputs: drop a 3-pixel border through ROI views
         imagePrev = imagePrev.roi(3, rows - 3, 3, cols - 3);
         imageNext = imageNext.roi(3, rows - 3, 3, cols - 3);
+    }
+    if (mode == "f32") {   // what cv::Mat::convertTo(CV_32F, 1.0 / 255) gives
+        cv::Mat fp(rows, cols, CV_32FC1), fn(rows, cols, CV_32FC1);
+        for (int y = 0; y < rows; ++y)
+            for (int x = 0; x < cols; ++x) {
+                fp.at<float>(y, x) = (float)(imagePrev.at<unsigned char>(y, x) * (1.0 / 255));
+                fn.at<float>(y, x) = (float)(imageNext.at<unsigned char>(y, x) * (1.0 / 255));
+            }
+        imagePrev = fp; imageNext = fn;
     }
     try {
         cv::Mat u, v;
@@ -28,6 +41,7 @@ int main(int argc, char** argv) {
         int maxIterations = atoi(argv[6]);
         double alpha = atof(argv[7]);
         hornSchunck hs = hornSchunck(windowSize, maxIterations, alpha);     // main.cpp:97
+        if (mode == "f64prec") hs.precision = HS_PREC_F64;
         hs.getFlow(imagePrev, imageNext, u, v);                            // main.cpp:98
         cv::Mat gx, gy, gt;
         hs.getGradients(imagePrev, imageNext, gx, gy, gt);

@@ -25,7 +25,7 @@
 #define CV_64FC1 CV_MAKETYPE(CV_64F, 1)
 
 namespace cv {
-namespace Error { enum { StsBadArg = -5, StsUnmatchedSizes = -209, StsUnsupportedFormat = -210, GpuApiCallError = -217 }; }
+namespace Error { enum { StsBadArg = -5, StsUnmatchedFormats = -205, StsUnmatchedSizes = -209, StsUnsupportedFormat = -210, GpuApiCallError = -217 }; }
 class Exception : public std::runtime_error {
 public:
     int code;

@@ -154,3 +154,28 @@ def test_slab_plan_is_pure_host_arithmetic(pkg):
     info = H.HsSlabInfo()
     assert lib.hs_plan_slab(40, 8, 0, 3, 6, ctypes.byref(info)) == 1      # 5-row slabs cannot hold a 6-row halo
     assert b"halo" in lib.hs_last_error(None)
+
+
+def test_default_k_is_near_the_measured_best(pkg):
+    """The temporal-blocking depth hs_create picks (hs_default_temporal_k: defaults measured for large frames, a
+    phase cost model for small ones) against the k sweep measured on B200 with this kernel
+    (profiles/r02n_k_sweep.jsonl, tools/gpu_sweep.py): within 5 % of the best k for every size and window."""
+    import collections
+    import json
+    from cpp_optical_flow_b200 import hs_ctypes as H
+    lib = pkg.load_library()
+    rows = [json.loads(l) for l in open(os.path.join(ROOT, "profiles", "r02n_k_sweep.jsonl")) if l.startswith("{")]
+    by = collections.defaultdict(dict)
+    for r in rows:
+        if "error" not in r:
+            by[(r["W"], r["H"], r["T"], r["w"])][r["k"]] = r["gpixit_s"]
+    assert len(by) >= 12
+    for (W, Hh, T, w), sweep in sorted(by.items()):
+        cfg = H.HsConfig(struct_size=ctypes.sizeof(H.HsConfig), width=W, height=Hh, window_size=w, max_iterations=T, alpha=1.0)
+        k = lib.hs_default_temporal_k(ctypes.byref(cfg), 148)
+        assert k in sweep, (W, Hh, w, k, sorted(sweep))
+        assert sweep[k] >= 0.95 * max(sweep.values()), (W, Hh, w, k, sweep[k], max(sweep.items(), key=lambda kv: kv[1]))
+    cfg = H.HsConfig(struct_size=ctypes.sizeof(H.HsConfig), width=640, height=480, window_size=11, max_iterations=10, alpha=1.0)
+    assert lib.hs_default_temporal_k(ctypes.byref(cfg), 148) == 0          # no fused kernel for w = 11
+    cfg.window_size, cfg.temporal_k = 3, 40
+    assert lib.hs_default_temporal_k(ctypes.byref(cfg), 148) == 18         # an explicit k is only clamped

@@ -23,10 +23,11 @@ def driver(tmp_path_factory, pkg):
     return exe
 
 
-def run_driver(exe, tmp_path, a, b, w, iters, alpha, roi=False):
+def run_driver(exe, tmp_path, a, b, w, iters, alpha, roi=False, mode=None):
     pa, pb, po = str(tmp_path / "a.raw"), str(tmp_path / "b.raw"), str(tmp_path / "o.bin")
     a.tofile(pa); b.tofile(pb)
-    args = [exe, pa, pb, str(a.shape[0]), str(a.shape[1]), str(w), str(iters), repr(alpha), po] + (["roi"] if roi else [])
+    args = [exe, pa, pb, str(a.shape[0]), str(a.shape[1]), str(w), str(iters), repr(alpha), po] + \
+        (["roi"] if roi else []) + ([mode] if mode else [])
     r = subprocess.run(args, capture_output=True, text=True)
     return r, po
 
@@ -56,3 +57,27 @@ def test_adapter_matches_oracle_and_python_mirror(driver, tmp_path, pkg, oracle,
     u, v = hs.getFlow(a, b)
     hs.close()
     assert np.array_equal(out[0], u) and np.array_equal(out[1], v)      # C++ and Python hosts: same library, same bits
+
+
+@pytest.mark.gpu
+def test_adapter_takes_float_frames_like_the_reference(driver, tmp_path, c_oracle, oracle):
+    """CV_32F frames in [0,1]: upstream converts any depth to CV_64FC1 (hornSchunck.cpp:23-24).  The adapter
+    routes them to the library's fp64 path; flow and gradients equal the fp64 oracle on the same values, bit
+    for bit.  The same path on 8-bit frames (hs.precision = HS_PREC_F64) equals OpenCV's own result."""
+    rng = np.random.default_rng(22)
+    a = rng.integers(0, 256, (70, 110), dtype=np.uint8)
+    b = np.clip(a.astype(int) + rng.integers(-15, 16, a.shape), 0, 255).astype(np.uint8)
+    r, po = run_driver(driver, tmp_path, a, b, 5, 50, 0.05, mode="f32")
+    assert r.returncode == 0, r.stdout + r.stderr
+    out = np.fromfile(po, np.float64).reshape(5, *a.shape)
+    fa, fb = (a * (1.0 / 255)).astype(np.float32), (b * (1.0 / 255)).astype(np.float32)
+    ou, ov = c_oracle.flow_real(fa.astype(np.float64), fb.astype(np.float64), 5, 50, 0.05)
+    assert np.abs(ou).max() > 1e-3
+    assert np.array_equal(out[0], ou) and np.array_equal(out[1], ov)
+    gx, gy, gt = oracle.np_gradients(fa.astype(np.float64), fb.astype(np.float64))
+    assert np.array_equal(out[2], gx) and np.array_equal(out[3], gy) and np.array_equal(out[4], gt)
+    r, po = run_driver(driver, tmp_path, a, b, 5, 50, 1.0, mode="f64prec")
+    assert r.returncode == 0, r.stdout + r.stderr
+    out = np.fromfile(po, np.float64).reshape(5, *a.shape)
+    *_, cu, cv_ = oracle.cv_flow(a, b, 5, 50, 1.0)
+    assert np.array_equal(out[0], cu) and np.array_equal(out[1], cv_)
