@@ -432,6 +432,26 @@ def run_ours(args, rank, local_rank, world):
                 "note": "32 B per pixel-iteration, no credit for temporal blocking: k fused sweeps per HBM round "
                         "trip is why frac can exceed 1"}
 
+    # The unit K3 is really bound by ("What bounds K3"): the FP32 pipe.  Lane-operations per STAGED
+    # pixel-sweep of the canonical arithmetic, the valid fraction of a staged 128 x 48 tile at this k, and the
+    # SM clock sampled under load give the pipe's roof for this configuration.
+    clk = clocks.summary()
+    if tm.kernel_id == 1 and not args.textbook and clk and clk.get("sm_mhz"):
+        a = window - window // 2 - 1
+        rl, rr, k = a, window - 1 - a, tm.temporal_k
+        adds = window / 2.0                               # adds of a paired window sum per pixel and direction (w=3: 1.5, w=5: 2.5)
+        lane_ops = 2 * 2 * adds + 2 + 5                   # u and v, two directions; mean scaling; the update
+        vx = 128 - ((rl * k + 3) // 4) * 4 - ((rr * k + 3) // 4) * 4
+        hyt = rl * k + ((rl * k) & 1)
+        vy = (48 - hyt - rr * k) & ~1
+        valid = max(vx, 0) * max(vy, 0) / (128.0 * 48.0)
+        sms = torch.cuda.get_device_properties(local_rank).multi_processor_count
+        roof = sms * 128 * clk["sm_mhz"] * 1e6 / lane_ops * valid / 1e6          # Mpixel-iter/s
+        roofline["fp32_pipe"] = {"lane_ops_per_staged_pixel_sweep": lane_ops, "valid_fraction_of_a_staged_tile": valid,
+                                 "roof_mpixel_iter_s": roof, "frac": (value / world) / roof,
+                                 "note": "128 FP32 lanes per SM and clock at the sampled SM clock; FADD2/FMUL2/FFMA2 occupy "
+                                         "the pipe for two cycles (tools/fp_pipe_probe.cu), so packing does not raise this roof"}
+
     cpu = None
     if world == 1 and not args.no_cpu and not args.textbook:
         # headline: ONE thread, as BASELINE configs[0] / BASELINE.md 4.3 specify; all host cores beside it

@@ -72,6 +72,7 @@ struct hs_ctx {
     void* d_out = nullptr;
     size_t out_bytes = 0;
     uint8_t* d_bgr = nullptr;    // staging for hs_solve_bgr: two 8UC3 frames
+    uint8_t* d_flat = nullptr;   // staging for dense host frames whose rows are not 128-byte multiples (do_upload)
     unsigned int* d_resid = nullptr;   // hs_iterate_until: max-abs-difference accumulator
     // streaming front-end (hs_video_*): frame ring, copy stream, double-buffered output staging
     uint8_t* d_ring[3] = {nullptr, nullptr, nullptr};   // [0], [1] are the context's own prev/next
@@ -446,6 +447,33 @@ int do_upload(hs_ctx* c, const uint8_t* prev, size_t ps, size_t pis, const uint8
     if (c->B > 1 && (pis < ps * c->frows || nis < ns * c->frows))
         return fail(c, HS_ERR_INVALID_ARG, "image stride smaller than one image");
     if (c->d_ring[0]) { c->d_prev = c->d_ring[0]; c->d_next = c->d_ring[1]; }   // leave streaming mode
+    const size_t rowb = (size_t)c->W * c->fes;
+    // A pitched host->device copy whose rows are not whole 128-byte lines is row-bound, not byte-bound
+    // (measured, profiles/r02q_memcpy_probe.txt: 60 us against 15 us for one 1242 x 375 frame).  Dense host
+    // frames therefore cross PCIe as ONE flat copy into a staging buffer and are re-pitched on the device
+    // (a device-to-device 2-D copy, a few microseconds).
+    if (rowb != c->fpitch && ps == rowb && ns == rowb) {
+        const size_t img = rowb * c->frows;
+        if (!c->d_flat) HS_CUDA(c, cudaMalloc(&c->d_flat, 2 * img * c->B));
+        const uint8_t* src[2] = {prev, next};
+        const size_t is[2] = {pis, nis};
+        uint8_t* dst[2] = {c->d_prev, c->d_next};
+        for (int f = 0; f < 2; ++f) {
+            uint8_t* flat = c->d_flat + (size_t)f * img * c->B;
+            if (c->B == 1 || is[f] == img) {
+                HS_CUDA(c, cudaMemcpyAsync(flat, src[f], img * c->B, cudaMemcpyHostToDevice, c->stream));
+            } else {
+                for (int b = 0; b < c->B; ++b)
+                    HS_CUDA(c, cudaMemcpyAsync(flat + (size_t)b * img, src[f] + (size_t)b * is[f], img, cudaMemcpyHostToDevice, c->stream));
+            }
+            for (int b = 0; b < c->B; ++b)
+                HS_CUDA(c, cudaMemcpy2DAsync(dst[f] + (size_t)b * c->fimg, c->fpitch, flat + (size_t)b * img, rowb, rowb, c->frows,
+                                             cudaMemcpyDeviceToDevice, c->stream));
+        }
+        c->uploaded = true;
+        c->prepared = false;
+        return HS_OK;
+    }
     for (int b = 0; b < c->B; ++b) {
         HS_CUDA(c, cudaMemcpy2DAsync(c->d_prev + (size_t)b * c->fimg, c->fpitch, prev + (size_t)b * pis, ps,
                                      (size_t)c->W * c->fes, c->frows, cudaMemcpyHostToDevice, c->stream));
@@ -656,7 +684,7 @@ void destroy_impl(hs_ctx* c) {
         if (c->ipc_up) cudaIpcCloseMemHandle(c->ipc_up);
         if (c->ipc_dn) cudaIpcCloseMemHandle(c->ipc_dn);
         cudaFree(c->arena);
-        cudaFree(c->d_cpk); cudaFree(c->d_inv); cudaFree(c->d_done); cudaFree(c->d_bgr); cudaFree(c->d_resid); cudaFree(c->d_out);
+        cudaFree(c->d_cpk); cudaFree(c->d_inv); cudaFree(c->d_done); cudaFree(c->d_bgr); cudaFree(c->d_flat); cudaFree(c->d_resid); cudaFree(c->d_out);
         for (auto& e : c->ev) if (e) cudaEventDestroy(e);
         if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
     }

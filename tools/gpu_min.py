@@ -1,4 +1,4 @@
-"""Smallest possible fused-kernel launch (for compute-sanitizer / debugging)."""
+"""Smallest possible fused-kernel launch (a debugging aid: one tile, a few sweeps)."""
 import os, sys
 import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
