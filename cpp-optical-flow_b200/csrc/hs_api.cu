@@ -180,6 +180,27 @@ int make_map(hs_ctx* c, CUtensorMap* m, void* base, CUtensorMapDataType dt, int 
     return HS_OK;
 }
 
+// The flow plane ({u, v} interleaved, 8 bytes per pixel) as a rank-4 map (32-byte chunk, chunk of the row, y,
+// pair) with SWIZZLE_32B.  The staged tile has the same linear layout as a rank-3 box, except that the two
+// 16-byte halves of a 32-byte chunk trade places in every other 128-byte line (address bit 4 ^= bit 7).  A lane's
+// four pixels are one 32-byte chunk; with the swizzle, lanes 0-3 and 4-7 of a quarter warp find the half they
+// want in different bank groups, so the two LDS.128 of a patch row are conflict-free (they were 2-way
+// conflicted: 8 % of the kernel's shared-memory wavefronts).  Columns W .. round_up(W, 4) of the last chunk
+// are read from the pad columns of the plane instead of being zero-filled: they are zero by construction
+// (memset at hs_prepare; the kernels only ever store zeros beyond column W).
+int make_map_uv(hs_ctx* c, CUtensorMap* m, void* base, int box_x_px, int box_y) {
+    auto enc = tensor_map_encoder();
+    if (!enc) return fail(c, HS_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+    cuuint64_t dims[4] = {8, (cuuint64_t)(c->W + 3) / 4, (cuuint64_t)c->H, (cuuint64_t)c->B};
+    cuuint64_t strides[3] = {32, (cuuint64_t)c->pitch * 8, (cuuint64_t)c->plane * 8};
+    cuuint32_t box[4] = {8, (cuuint32_t)box_x_px / 4, (cuuint32_t)box_y, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(c, HS_ERR_CUDA, "cuTensorMapEncodeTiled (flow plane) failed (CUresult %d)", (int)r);
+    return HS_OK;
+}
+
 int env_int(const char* name, int dflt) {
     const char* s = getenv(name);
     return (s && *s) ? atoi(s) : dflt;
@@ -888,7 +909,7 @@ int create_single(const hs_config& cfg_in, hs_ctx** out) {
         int rc;
         for (int i = 0; i < 2; ++i) {
             // {u, v} interleaved: a float plane 2*W wide, box 2*SX floats (256 = the TMA box limit)
-            if ((rc = make_map(c, &c->tm_uv[i], c->d_uv[i], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, 2 * TS0::SX, TS0::SY, 2))) return bail(rc);
+            if ((rc = make_map_uv(c, &c->tm_uv[i], c->d_uv[i], TS0::SX, TS0::SY))) return bail(rc);
         }
         if ((rc = make_map(c, &c->tm_cpk, c->d_cpk, CU_TENSOR_MAP_DATA_TYPE_UINT32, 4, TS0::SX, TS0::SY))) return bail(rc);
         if ((rc = make_map(c, &c->tm_inv, c->d_inv, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, TS0::SX, TS0::SY))) return bail(rc);

@@ -387,6 +387,15 @@ __device__ __forceinline__ void pdl_launch_dependents() {
 __device__ __forceinline__ void pdl_wait() {
     asm volatile("griddepcontrol.wait;" ::: "memory");
 }
+// 4-D tiled load (32-byte chunk, chunk, y, pair): the swizzled flow-plane map (make_map_uv in hs_api.cu)
+__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, uint64_t* bar,
+                                            int c0, int c1, int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes"
+        " [%0], [%1, {%2, %3, %4, %5}], [%6];" ::"r"(smem_u32(dst)),
+        "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(smem_u32(bar))
+        : "memory");
+}
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
 }
@@ -700,7 +709,7 @@ struct FastDiv {
     __device__ __forceinline__ int div(int n) const { return d == 1 ? n : (int)(__umulhi((uint32_t)n, mul) >> shr); }
 };
 struct SlabDesc {
-    CUtensorMap tm_uv[2], tm_cpk, tm_inv;   // tm_uv: the flow plane as a float plane 2*W wide ({u, v} interleaved)
+    CUtensorMap tm_uv[2], tm_cpk, tm_inv;   // tm_uv: the flow plane in 32-byte chunks of 4 pixels ({u, v} interleaved), SWIZZLE_32B
     float2* uv[2];
     Geom g;                    // oy0 / oy1 = the rows this launch produces
     int hyt, vy;               // halo rows above the stored centre of a tile; rows of the centre
@@ -821,7 +830,7 @@ k_jacobi_tile(const __grid_constant__ LaunchDesc<MAXS> d) {
     static_assert(R * 4 <= 32, "in-image mask is one 32-bit word per thread");
     static_assert(RL <= 4 && RR <= 4, "horizontal neighbours come from the adjacent lane only");
     static_assert(NWARP % 4 == 0, "setmaxnreg acts on whole warp groups");
-    extern __shared__ __align__(128) unsigned char smem[];
+    extern __shared__ __align__(1024) unsigned char smem[];
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + TS::OFF_BAR);  // TMA bytes landed      [2]
     uint64_t* empty = full + 2;                                        // stage may be refilled [2]
     uint64_t* stored = full + 4;                                       // tile results stored   [2]
@@ -911,7 +920,7 @@ k_jacobi_tile(const __grid_constant__ LaunchDesc<MAXS> d) {
             mbar_expect_tx(&full[stage], TS::TX_BYTES);
             tma_load_3d(st + TS::OFF_CPK, &S.tm_cpk, &full[stage], it.x0, it.y0, it.b);
             tma_load_3d(st + TS::OFF_INV, &S.tm_inv, &full[stage], it.x0, it.y0, it.b);
-            tma_load_3d(st + TS::OFF_UV, &S.tm_uv[rd], &full[stage], 2 * it.x0, it.y0, it.b);
+            tma_load_4d(st + TS::OFF_UV, &S.tm_uv[rd], &full[stage], 0, it.x0 >> 2, it.y0, it.b);   // x0 is a multiple of 4 (may be negative)
         };
         if (lane == 0) {
 #pragma unroll
@@ -1102,12 +1111,15 @@ k_jacobi_tile(const __grid_constant__ LaunchDesc<MAXS> d) {
                 }
         }
 
+        const int swz = ((smem_u32(s_uv) >> 7) ^ (lane >> 2)) & 1;   // address bit 7 of the lane's chunk (rows are 1 KB)
         float2 uv[R][4], gxy[R][4];        // {u, v} and {Ix, Iy} per pixel: packed-fp32 operands
         float it[R][4], iv[R][4];
 #pragma unroll
         for (int j = 0; j < R; ++j) {
             const int so = (row0 + j) * TS::SX + lane * 4;
-            const float4 q0 = s_uv[so / 2], q1 = s_uv[so / 2 + 1];
+            // the lane's 32-byte chunk; SWIZZLE_32B put its first half into the upper 16 bytes in every other
+            // 128-byte line (lanes 4-7 of each group of 8): reading "my first half" is then conflict-free
+            const float4 q0 = s_uv[so / 2 + swz], q1 = s_uv[so / 2 + (swz ^ 1)];
             const float4 qi = *reinterpret_cast<const float4*>(s_inv + so);
             const uint4 qc = *reinterpret_cast<const uint4*>(s_cpk + so);
             uv[j][0] = make_float2(q0.x, q0.y); uv[j][1] = make_float2(q0.z, q0.w);
