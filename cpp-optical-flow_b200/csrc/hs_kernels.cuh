@@ -47,10 +47,17 @@ struct Geom {
 __device__ __forceinline__ uint32_t pack_coef(int gx, int gy, int gt) {
     return ((uint32_t)(gx + 1024) << 21) | ((uint32_t)(gy + 1024) << 10) | (uint32_t)(gt + 512);
 }
+// (a & mask) | magic as ONE LOP3 (truth table 0xEA); written as asm because the compiler, given two literal
+// constants, emits two LOP3s with an immediate each (2 of the 9 unpack instructions per pixel)
+__device__ __forceinline__ uint32_t and_or(uint32_t a, uint32_t mask, uint32_t magic) {
+    uint32_t d;
+    asm("lop3.b32 %0, %1, %2, %3, 0xEA;" : "=r"(d) : "r"(a), "r"(mask), "r"(magic));
+    return d;
+}
 __device__ __forceinline__ void unpack_coef(uint32_t w, float& ix, float& iy, float& it) {
     ix = __fsub_rn(__uint_as_float((w >> 21) | 0x4B000000u), 8389632.0f);            // 2^23 + 1024
-    iy = __fsub_rn(__uint_as_float(((w >> 10) & 0x7ffu) | 0x4B000000u), 8389632.0f);
-    it = __fsub_rn(__uint_as_float((w & 0x3ffu) | 0x4B000000u), 8389120.0f);         // 2^23 + 512
+    iy = __fsub_rn(__uint_as_float(and_or(w >> 10, 0x7ffu, 0x4B000000u)), 8389632.0f);
+    it = __fsub_rn(__uint_as_float(and_or(w, 0x3ffu, 0x4B000000u)), 8389120.0f);     // 2^23 + 512
 }
 
 __device__ __forceinline__ int reflect101(int i, int n) {
