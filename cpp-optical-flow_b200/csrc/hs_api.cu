@@ -209,18 +209,23 @@ int env_int(const char* name, int dflt) {
 // Temporal-blocking depth k (sweeps fused per phase) of the fused kernel: pure host arithmetic, exported
 // as hs_default_temporal_k so that the choice can be checked against the measured sweeps in profiles/.
 //   `asked` > 0: the caller's k, only clamped to what a 128 x 48 staged tile can hold.
-//   Large frames: measured on B200 (profiles/*k_sweep*, profiles/*traffic_table*): radius-1 windows want
-//   k=6 when the planes stream from HBM (fewer bytes per sweep) but k=4 when the 24 B/pixel working set sits
-//   in L2 (better valid fraction per staged tile); radius-2 windows k=3; radius 3..4 (w = 6..9) k=2.
-//   Small and medium frames (less than four tiles per SM) choose k from a cost model of a phase
-//   (microseconds, fitted on B200: profiles/r01j_k_sweep_kitti.jsonl, r01j_k_sweep_mid.jsonl; re-checked against
-//   profiles/r02n_k_sweep.jsonl by tests/test_abi_cpu.py::test_default_k_is_near_the_measured_best):
+//   Large frames: measured on B200 (profiles/r02w_k_sweep*.jsonl, k = 1..12 for every window that has a fused
+//   kernel; DRAM side in profiles/*traffic_table*): w=2 k=8, w=3 k=6, w=4 k=4, w=5 k=3, w=6..9 k=2.  (Until the
+//   tile load lost its bank conflicts, w=3 wanted k=4 while the working set sat in L2; now a staged tile is
+//   cheap enough to load that the deeper k wins everywhere.)
+//   Small and medium frames (less than three tiles per SM) choose k from a cost model of a phase
+//   (microseconds, fitted on B200 to profiles/r02w_k_sweep.jsonl and checked against it by
+//   tests/test_abi_cpu.py::test_default_k_is_near_the_measured_best):
 //     a tile costs          item(k)  = k * t_sweep + t_tile
 //     chained launches      phase(k) = ceil(tiles / #SMs) * item + t_launch     (tiles < 1.25 #SMs)
 //     one dataflow launch   phase(k) = max(tiles / #SMs * item, item + t_dep)
-//   and the k with the lowest phase(k) / k wins.  t_dep is the publish -> poll -> TMA chain from a finished
+//   and the k with the lowest ceil(T / k) * phase(k) (+ t_coop for a dataflow launch) wins.  t_dep is the publish -> poll -> TMA chain from a finished
 //   tile to its dependants: with few tiles per SM it, not the arithmetic, paces a phase, and fusing more
 //   sweeps per phase amortises it.
+inline int large_frame_k(int RL, int RR) {
+    const int w = RL + RR + 1;
+    return w <= 2 ? 8 : (w == 3 ? 6 : (w == 4 ? 4 : (w == 5 ? 3 : 2)));
+}
 int choose_temporal_k(int asked, int W, int rows, int row_parity, int B, int RL, int RR, int max_iterations, int num_sms,
                       bool may_dataflow, bool seam, double plane_px) {
     const int SY = TILE_R * TILE_NWARP, SX = 128;
@@ -234,18 +239,16 @@ int choose_temporal_k(int asked, int W, int rows, int row_parity, int B, int RL,
         return (size_t)((W + vx - 1) / vx) * ((rows + vy - 1) / vy) * B;
     };
     int k = asked;
-    if (k <= 0) {
-        const bool l2_resident = plane_px * 24.0 <= 64.0e6;
-        k = rad <= 1 ? (l2_resident ? 4 : 6) : (rad == 2 ? 3 : 2);
-    }
+    if (k <= 0) k = large_frame_k(RL, RR);
+    (void)plane_px;
     k = std::min(k, kmax);
     // keep a useful centre: at least a quarter of the staged rows must be output rows
     while (k > 1 && SY - (RL + RR) * k < SY / 4) --k;
-    if (asked <= 0 && !seam && tiles(k) < (size_t)4 * num_sms) {
-        // (t_dep was 7.5 us while the producer warp paid two MEMBARs per dependency check; 5 us with acquire loads)
-        const double t_sweep = rad <= 1 ? 0.59 : 0.97, t_tile = 1.5, t_launch = 2.4, t_dep = 5.0;
-        int kcap = std::min(kmax, rad <= 1 ? 12 : 6);
+    if (asked <= 0 && !seam && tiles(k) < (size_t)3 * num_sms) {
+        const double t_sweep = rad <= 1 ? 0.45 : 0.8, t_tile = 1.2, t_launch = 3.0, t_dep = 6.0, t_coop = 40.0;
+        int kcap = std::min(kmax, rad <= 1 ? 12 : 7);
         if (max_iterations > 0) kcap = std::min(kcap, max_iterations);
+        const int T = max_iterations > 0 ? max_iterations : 1000;
         double best = 1e300;
         for (int kk = 1; kk <= kcap; ++kk) {
             if (kk > 1 && SY - (RL + RR) * kk < SY / 4) break;
@@ -255,7 +258,11 @@ int choose_temporal_k(int asked, int W, int rows, int row_parity, int B, int RL,
             const bool dataflow = may_dataflow && n * 4 >= (size_t)num_sms * 5;
             const double phase = dataflow ? std::max((double)n / num_sms * item, item + t_dep)
                                           : (double)((n + num_sms - 1) / num_sms) * item + t_launch;
-            if (phase / kk < best) { best = phase / kk; k = kk; }
+            // whole solve: ceil(T / k) phases (the last one may be short but costs a full tile round), plus the
+            // fixed cost of the cooperative launch (launch + counter memset + descriptor prefetch: ~40 us measured
+            // on the bundled pair, profiles/r02y_traffic_table.txt: k=7 206 against k=4 243 Gpix-it/s at T=100)
+            const double total = (double)((T + kk - 1) / kk) * phase + (dataflow ? t_coop : 0.0);
+            if (total < best) { best = total; k = kk; }
         }
     }
     return k;

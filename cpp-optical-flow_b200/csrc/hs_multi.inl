@@ -50,10 +50,8 @@ bool plan_slab(int H, int world, int rank, int RL, int RR, int k, SlabPlan* p, s
 int pick_slab_k(const hs_config& cfg, int RL, int RR, int rows) {
     int k = cfg.temporal_k > 0 ? cfg.temporal_k : env_int("HS_K", 0);
     const int rad = std::max(RL, RR);
-    if (k <= 0) {
-        const bool l2_resident = (double)round_up(cfg.width, 32) * rows * 24.0 <= 64.0e6;
-        k = rad <= 1 ? (l2_resident ? 4 : 6) : (rad == 2 ? 3 : 2);
-    }
+    if (k <= 0) k = large_frame_k(RL, RR);
+    (void)rows; (void)rad;
     const int SY = TILE_R * TILE_NWARP;
     k = std::min(k, (SY - 3) / std::max(1, RL + RR));
     while (k > 1 && SY - (RL + RR) * k < SY / 4) --k;

@@ -77,6 +77,8 @@ def load_library(path: str | None = None):
     global _lib
     if _lib is not None and path is None:
         return _lib
+    if path is None and os.environ.get("HS_B200_LIB"):
+        path = os.environ["HS_B200_LIB"]          # an A/B build of the same CUDA library (tools/variant_build.sh)
     if path is None:
         path = _build.LIB
         if _build.is_stale() and _build.nvcc_path():

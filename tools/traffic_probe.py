@@ -24,6 +24,8 @@ for k in (1, 2, 3, 4, 6):
     CASES.append(("4k", 2160, 3840, 1, 5, k, SWEEPS if k != 6 else 48))
 CASES.append(("1080p", 1080, 1920, 1, 3, 4, 1000))        # the headline launch itself (L2-resident)
 CASES.append(("1080p", 1080, 1920, 1, 5, 3, 999))
+CASES.append(("1080p", 1080, 1920, 1, 3, 6, 996))         # the default k since the r02w sweep
+CASES.append(("kitti", 375, 1242, 1, 5, 7, 98))
 CASES.append(("batch256", 1080, 1920, 4, 3, 6, SWEEPS))   # 4 pairs per launch = 200 MB working set
 CASES.append(("batch256", 1080, 1920, 4, 3, 4, SWEEPS))
 CASES.append(("kitti", 375, 1242, 1, 5, 4, 100))
