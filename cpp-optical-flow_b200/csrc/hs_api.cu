@@ -79,6 +79,9 @@ struct hs_ctx {
     void* d_vout[2] = {nullptr, nullptr};
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t ev_up = nullptr, ev_k1[3] = {nullptr, nullptr, nullptr}, ev_solved[2] = {nullptr, nullptr};
+    cudaEvent_t ev_async[2] = {nullptr, nullptr};   // hs_solve_async: frames uploaded / flow staged
+    bool async_pending = false;
+    cudaStream_t xfer = nullptr; // stream the host<->device copies of do_upload / do_download go to (null = `stream`)
     int vid_frames = 0;          // frames pushed so far
     int vid_pending = -1;        // pair solved (or being solved) whose flow was not handed out yet
     int vid_dtype = -1;
@@ -475,6 +478,7 @@ int do_upload(hs_ctx* c, const uint8_t* prev, size_t ps, size_t pis, const uint8
     if (c->B > 1 && (pis < ps * c->frows || nis < ns * c->frows))
         return fail(c, HS_ERR_INVALID_ARG, "image stride smaller than one image");
     if (c->d_ring[0]) { c->d_prev = c->d_ring[0]; c->d_next = c->d_ring[1]; }   // leave streaming mode
+    cudaStream_t cs = c->xfer ? c->xfer : c->stream;
     const size_t rowb = (size_t)c->W * c->fes;
     // A pitched host->device copy whose rows are not whole 128-byte lines is row-bound, not byte-bound
     // (measured, profiles/r02q_memcpy_probe.txt: 60 us against 15 us for one 1242 x 375 frame).  Dense host
@@ -489,14 +493,14 @@ int do_upload(hs_ctx* c, const uint8_t* prev, size_t ps, size_t pis, const uint8
         for (int f = 0; f < 2; ++f) {
             uint8_t* flat = c->d_flat + (size_t)f * img * c->B;
             if (c->B == 1 || is[f] == img) {
-                HS_CUDA(c, cudaMemcpyAsync(flat, src[f], img * c->B, cudaMemcpyHostToDevice, c->stream));
+                HS_CUDA(c, cudaMemcpyAsync(flat, src[f], img * c->B, cudaMemcpyHostToDevice, cs));
             } else {
                 for (int b = 0; b < c->B; ++b)
-                    HS_CUDA(c, cudaMemcpyAsync(flat + (size_t)b * img, src[f] + (size_t)b * is[f], img, cudaMemcpyHostToDevice, c->stream));
+                    HS_CUDA(c, cudaMemcpyAsync(flat + (size_t)b * img, src[f] + (size_t)b * is[f], img, cudaMemcpyHostToDevice, cs));
             }
             for (int b = 0; b < c->B; ++b)
                 HS_CUDA(c, cudaMemcpy2DAsync(dst[f] + (size_t)b * c->fimg, c->fpitch, flat + (size_t)b * img, rowb, rowb, c->frows,
-                                             cudaMemcpyDeviceToDevice, c->stream));
+                                             cudaMemcpyDeviceToDevice, cs));
         }
         c->uploaded = true;
         c->prepared = false;
@@ -504,9 +508,9 @@ int do_upload(hs_ctx* c, const uint8_t* prev, size_t ps, size_t pis, const uint8
     }
     for (int b = 0; b < c->B; ++b) {
         HS_CUDA(c, cudaMemcpy2DAsync(c->d_prev + (size_t)b * c->fimg, c->fpitch, prev + (size_t)b * pis, ps,
-                                     (size_t)c->W * c->fes, c->frows, cudaMemcpyHostToDevice, c->stream));
+                                     (size_t)c->W * c->fes, c->frows, cudaMemcpyHostToDevice, cs));
         HS_CUDA(c, cudaMemcpy2DAsync(c->d_next + (size_t)b * c->fimg, c->fpitch, next + (size_t)b * nis, ns,
-                                     (size_t)c->W * c->fes, c->frows, cudaMemcpyHostToDevice, c->stream));
+                                     (size_t)c->W * c->fes, c->frows, cudaMemcpyHostToDevice, cs));
     }
     c->uploaded = true;
     c->prepared = false;
@@ -606,12 +610,18 @@ int do_download(hs_ctx* c, void* u, size_t us, size_t uis, void* v, size_t vs, s
     }
     HS_CUDA(c, cudaGetLastError());
     c->timing.launches += 1;
+    cudaStream_t cs = c->stream;
+    if (c->xfer) {                 // hs_solve_async: the device->host copies leave on the transfer stream
+        HS_CUDA(c, cudaEventRecord(c->ev_async[1], c->stream));
+        HS_CUDA(c, cudaStreamWaitEvent(c->xfer, c->ev_async[1], 0));
+        cs = c->xfer;
+    }
     for (int b = 0; b < c->B; ++b) {
         const size_t off = ((size_t)b * c->plane + (size_t)c->oy0 * c->pitch) * es;
         HS_CUDA(c, cudaMemcpy2DAsync(static_cast<char*>(u) + (size_t)b * uis, us, su + off, (size_t)c->pitch * es,
-                                     c->W * es, rows, cudaMemcpyDeviceToHost, c->stream));
+                                     c->W * es, rows, cudaMemcpyDeviceToHost, cs));
         HS_CUDA(c, cudaMemcpy2DAsync(static_cast<char*>(v) + (size_t)b * vis, vs, sv + off, (size_t)c->pitch * es,
-                                     c->W * es, rows, cudaMemcpyDeviceToHost, c->stream));
+                                     c->W * es, rows, cudaMemcpyDeviceToHost, cs));
     }
     return HS_OK;
 }
@@ -709,6 +719,7 @@ void destroy_impl(hs_ctx* c) {
         if (c->ev_up) cudaEventDestroy(c->ev_up);
         for (auto& e : c->ev_k1) if (e) cudaEventDestroy(e);
         for (auto& e : c->ev_solved) if (e) cudaEventDestroy(e);
+        for (auto& e : c->ev_async) if (e) cudaEventDestroy(e);
         if (c->ipc_up) cudaIpcCloseMemHandle(c->ipc_up);
         if (c->ipc_dn) cudaIpcCloseMemHandle(c->ipc_dn);
         cudaFree(c->arena);
@@ -1128,6 +1139,55 @@ int hs_solve(hs_ctx* c, const uint8_t* prev, size_t ps, size_t pis, const uint8_
     return HS_OK;
 }
 
+// hs_solve without the wait.  Host<->device copies run on a transfer stream of the context, the kernels on its
+// compute stream (hs_config.stream), ordered by events: contexts that share ONE compute stream therefore run their
+// kernels back to back in call order while the copies of one overlap the sweeps of the other.
+int hs_solve_async(hs_ctx* c, const uint8_t* prev, size_t ps, size_t pis, const uint8_t* next, size_t ns, size_t nis,
+                   void* u, size_t us, size_t uis, void* v, size_t vs, size_t vis, int dt) {
+    if (!c) return HS_ERR_INVALID_ARG;
+    HS_NO_GROUP(c, "hs_solve_async");
+    HS_NO_F64(c, "hs_solve_async");
+    if (c->top_seam || c->bot_seam) return fail(c, HS_ERR_UNSUPPORTED, "hs_solve_async needs a whole-image context");
+    if (c->async_pending) return fail(c, HS_ERR_STATE, "hs_solve_async: the previous call was not waited for (hs_solve_wait)");
+    DevGuard g(c->dev);
+    if (!c->copy_stream) HS_CUDA(c, cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    for (auto& e : c->ev_async)
+        if (!e) HS_CUDA(c, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    c->timing.launches = 0;
+    // the transfer stream must not overwrite the frames / the output staging while an earlier solve of this
+    // context still uses them: hs_solve_wait (or hs_sync) has returned, so there is none
+    c->xfer = c->copy_stream;
+    int rc = do_upload(c, prev, ps, pis, next, ns, nis);
+    if (!rc) {
+        cudaError_t e = cudaEventRecord(c->ev_async[0], c->xfer);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(c->stream, c->ev_async[0], 0);
+        if (e == cudaSuccess) e = cudaEventRecord(c->ev[1], c->stream);
+        if (e != cudaSuccess) rc = fail(c, HS_ERR_CUDA, "hs_solve_async: %s", cudaGetErrorString(e));
+    }
+    if (!rc) rc = do_prepare(c);
+    if (!rc && cudaEventRecord(c->ev[2], c->stream) != cudaSuccess) rc = fail(c, HS_ERR_CUDA, "cudaEventRecord failed");
+    if (!rc) rc = do_iterate(c, c->T);
+    if (!rc && cudaEventRecord(c->ev[3], c->stream) != cudaSuccess) rc = fail(c, HS_ERR_CUDA, "cudaEventRecord failed");
+    if (!rc) rc = do_download(c, u, us, uis, v, vs, vis, dt);
+    c->xfer = nullptr;
+    if (rc) return rc;
+    c->async_pending = true;
+    return HS_OK;
+}
+
+int hs_solve_wait(hs_ctx* c) {
+    if (!c) return HS_ERR_INVALID_ARG;
+    if (!c->async_pending) return HS_OK;
+    DevGuard g(c->dev);
+    HS_CUDA(c, cudaStreamSynchronize(c->copy_stream));    // the last copy waits for everything before it
+    c->async_pending = false;
+    c->timing.h2d_ms = c->timing.d2h_ms = 0.f;
+    c->timing.prepare_ms = ev_ms(c->ev[1], c->ev[2]);
+    c->timing.iterate_ms = ev_ms(c->ev[2], c->ev[3]);
+    c->timing.total_ms = ev_ms(c->ev[1], c->ev[3]);
+    return HS_OK;
+}
+
 int hs_solve_bgr(hs_ctx* c, const uint8_t* prev, size_t ps, const uint8_t* next, size_t ns,
                  void* u, size_t us, void* v, size_t vs, int dt) {
     if (!c) return HS_ERR_INVALID_ARG;
@@ -1296,8 +1356,8 @@ int video_setup(hs_ctx* c, int dt) {
     if (c->B != 1 || c->top_seam || c->bot_seam)
         return fail(c, HS_ERR_UNSUPPORTED, "hs_video_* needs a whole-image, batch == 1 context");
     if (dt != HS_F32 && dt != HS_F64) return fail(c, HS_ERR_INVALID_ARG, "bad out_dtype");
-    if (!c->copy_stream) {
-        HS_CUDA(c, cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    if (!c->ev_up) {
+        if (!c->copy_stream) HS_CUDA(c, cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
         HS_CUDA(c, cudaEventCreateWithFlags(&c->ev_up, cudaEventDisableTiming));
         for (auto& e : c->ev_k1) HS_CUDA(c, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
         for (auto& e : c->ev_solved) HS_CUDA(c, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));

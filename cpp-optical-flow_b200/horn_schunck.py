@@ -181,6 +181,14 @@ class Solver:
                                        u.ctypes.data, rs, ims, v.ctypes.data, rs, ims, dt))
         return u, v
 
+    def solve_async_raw(self, prev_ptr, next_ptr, row_stride, img_stride, u_ptr, v_ptr, out_row_stride, out_img_stride, dt):
+        """hs_solve_async on raw (page-locked) host pointers; pair with solve_wait()."""
+        self._check(self._lib.hs_solve_async(self._ctx, prev_ptr, row_stride, img_stride, next_ptr, row_stride, img_stride,
+                                             u_ptr, out_row_stride, out_img_stride, v_ptr, out_row_stride, out_img_stride, dt))
+
+    def solve_wait(self):
+        self._check(self._lib.hs_solve_wait(self._ctx))
+
     def solve_bgr(self, prev_bgr, next_bgr, out_dtype=np.float64):
         """preprocess() + getFlow (main.cpp:11-26,84,98): 8UC3 BGR frames in, BGR2GRAY on the device."""
         p = np.asarray(prev_bgr)

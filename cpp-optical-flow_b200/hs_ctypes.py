@@ -20,7 +20,7 @@ STATUS_NAMES = {0: "HS_OK", 1: "HS_ERR_INVALID_ARG", 2: "HS_ERR_CUDA", 3: "HS_ER
                 4: "HS_ERR_UNSUPPORTED", 5: "HS_ERR_STATE", 6: "HS_ERR_NCCL"}
 
 # every extern "C" symbol include/hs.h declares (tests check the library exports all of them)
-SYMBOLS = ["hs_create", "hs_destroy", "hs_solve", "hs_solve_bgr", "hs_gradients", "hs_upload", "hs_prepare",
+SYMBOLS = ["hs_create", "hs_destroy", "hs_solve", "hs_solve_async", "hs_solve_wait", "hs_solve_bgr", "hs_gradients", "hs_upload", "hs_prepare",
            "hs_iterate", "hs_iterate_rows", "hs_iterate_until", "hs_solve_device", "hs_download", "hs_sync", "hs_sample_grid", "hs_get_device_view",
            "hs_video_push", "hs_video_flush", "hs_video_reset", "hs_get_timing", "hs_last_error", "hs_version", "hs_host_alloc", "hs_host_free",
            "hs_get_slab_info", "hs_plan_slab", "hs_slab_export", "hs_slab_connect", "hs_default_temporal_k"]
@@ -92,6 +92,8 @@ def load_library(path: str | None = None):
     lib.hs_destroy.argtypes = [vp]
     lib.hs_destroy.restype = None
     lib.hs_solve.argtypes = [vp, vp, sz, sz, vp, sz, sz, vp, sz, sz, vp, sz, sz, i32]
+    lib.hs_solve_async.argtypes = [vp, vp, sz, sz, vp, sz, sz, vp, sz, sz, vp, sz, sz, i32]
+    lib.hs_solve_wait.argtypes = [vp]
     lib.hs_gradients.argtypes = [vp, vp, sz, vp, sz, vp, vp, vp, sz, i32]
     lib.hs_solve_bgr.argtypes = [vp, vp, sz, vp, sz, vp, sz, vp, sz, i32]
     lib.hs_upload.argtypes = [vp, vp, sz, sz, vp, sz, sz]

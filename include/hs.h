@@ -188,6 +188,22 @@ int hs_solve(hs_ctx* ctx,
              void* v, size_t v_row_stride, size_t v_image_stride,
              int out_dtype);
 
+/* hs_solve split in two so that independent pairs can overlap: hs_solve_async queues upload, solve and download and
+ * returns; hs_solve_wait blocks until the flow of that call is in u, v.  The host<->device copies run on a transfer
+ * stream owned by the context, the kernels on its compute stream (hs_config.stream): give several contexts the SAME
+ * compute stream and their kernels run back to back in call order while the copies of one call overlap the sweeps
+ * of the next (bench.py: `e2e.value_two_contexts_in_flight`, the batch256 workload).  Use page-locked host buffers
+ * (hs_host_alloc), keep them untouched until hs_solve_wait, and have at most one call per context in flight; any
+ * other work queued on the context (hs_solve_device ...) must have been waited for with hs_sync first.
+ * Single-device HS_PREC_F32 whole-image contexts. */
+int hs_solve_async(hs_ctx* ctx,
+                   const uint8_t* prev, size_t prev_row_stride, size_t prev_image_stride,
+                   const uint8_t* next, size_t next_row_stride, size_t next_image_stride,
+                   void* u, size_t u_row_stride, size_t u_image_stride,
+                   void* v, size_t v_row_stride, size_t v_image_stride,
+                   int out_dtype);
+int hs_solve_wait(hs_ctx* ctx);
+
 /* preprocess() + getFlow in one call (HornSchunckOF/main.cpp:11-26,84 then :98): prev/next are 8UC3
  * BGR frames (row stride >= 3*width bytes, a multiple of 4); the BGR2GRAY conversion runs on the
  * device with OpenCV's fixed-point luma (bit-exact with cv::cvtColor).  batch == 1 contexts. */

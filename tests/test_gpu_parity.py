@@ -345,6 +345,43 @@ def test_batch_equals_single_solves(pkg):
         assert np.array_equal(bu[i], u) and np.array_equal(bv[i], v)
 
 
+def test_async_solves_on_a_shared_stream_equal_synchronous_solves(pkg):
+    """hs_solve_async / hs_solve_wait: two contexts on ONE compute stream, two calls in flight, several rounds;
+    every flow equals the synchronous hs_solve of the same pair bit for bit, and a second call on a busy context
+    is refused."""
+    import torch
+    from cpp_optical_flow_b200 import hs_ctypes as H
+    Hh, Ww = 333, 517                                         # rows of 517 bytes: the flat-upload path too
+    pairs = [rand_pair((Hh, Ww), 70 + i) for i in range(5)]
+    want = []
+    with pkg.Solver(Ww, Hh, 3, 29, 1.0) as s:
+        for a, b in pairs:
+            want.append(s.solve(a, b, np.float64))
+    stream = torch.cuda.Stream()
+    hp = [torch.from_numpy(np.ascontiguousarray(a)).pin_memory() for a, _ in pairs]
+    hn = [torch.from_numpy(np.ascontiguousarray(b)).pin_memory() for _, b in pairs]
+    outs = [(torch.empty((Hh, Ww), dtype=torch.float64).pin_memory(), torch.empty((Hh, Ww), dtype=torch.float64).pin_memory())
+            for _ in range(2)]
+    ctxs = [pkg.Solver(Ww, Hh, 3, 29, 1.0, stream=stream.cuda_stream) for _ in range(2)]
+
+    def enqueue(i):
+        ou, ov = outs[i & 1]
+        ctxs[i & 1].solve_async_raw(hp[i].data_ptr(), hn[i].data_ptr(), Ww, 0, ou.data_ptr(), ov.data_ptr(), Ww * 8, 0, H.HS_F64)
+
+    enqueue(0)
+    with pytest.raises(H.HsError):
+        ctxs[0].solve_async_raw(hp[0].data_ptr(), hn[0].data_ptr(), Ww, 0, outs[0][0].data_ptr(), outs[0][1].data_ptr(), Ww * 8, 0, H.HS_F64)
+    for i in range(len(pairs)):
+        if i + 1 < len(pairs):
+            enqueue(i + 1)
+        ctxs[i & 1].solve_wait()
+        ou, ov = outs[i & 1]
+        assert np.array_equal(ou.numpy(), want[i][0]) and np.array_equal(ov.numpy(), want[i][1]), i
+    ctxs[0].solve_wait()                                      # nothing pending: a no-op
+    for c in ctxs:
+        c.close()
+
+
 def test_strided_inputs(pkg):
     big_a, big_b = rand_pair((90, 300), 9)
     a, b = big_a[:, 10:210], big_b[:, 10:210]            # row stride 300, width 200
