@@ -15,7 +15,9 @@
 //   the same rule combines the row sums down a column (pairs start at even absolute rows).  A pair
 //   sum is shared by the two windows that contain it: 1.5 instead of 2 adds per pixel and
 //   direction for w=3, 2.5 instead of 4 for w=5.
-//   ubar = S_u * fl(1/w^2);  vbar likewise
+//   ubar = S_u * fl(1/w^2);  vbar likewise - except for w = 3, where the column window is always ONE pair of rows and
+//   ONE single row: ubar = fma(single, kf, kf * pair) with kf = fl(1/9), so that the fused kernel multiplies each
+//   shared pair sum once for the two rows that use it (6 % less FP32-pipe work per sweep, +3 % throughput)
 //   t = fma(Ix, ubar, fma(Iy, vbar, It));  c = t * inv;  u' = fma(-Ix, c, ubar);  v' = fma(-Iy, c, vbar)
 // with inv = 1 / (fl(alpha^2) + (Ix^2 + Iy^2)) rounded once (IEEE division) in K1.
 // Explicit __f*_rn intrinsics keep the compiler from re-associating or contracting differently
@@ -294,13 +296,27 @@ k_jacobi_generic(const float2* __restrict__ uv, float2* __restrict__ uvn,
     float2 s = make_float2(0.f, 0.f);
     bool first = true;
     auto add = [&](float2 t) { s = first ? t : add2s(s, t); first = false; };
-    if ((r + g.grow0) & 1) { add(row_sum(r)); ++r; }
-    for (; r + 1 <= hi; r += 2) add(add2s(row_sum(r), row_sum(r + 1)));
-    if (r == hi) add(row_sum(r));
+    if (w != 3) {                                        // (w = 3 has its own rule below)
+        if ((r + g.grow0) & 1) { add(row_sum(r)); ++r; }
+        for (; r + 1 <= hi; r += 2) add(add2s(row_sum(r), row_sum(r + 1)));
+        if (r == hi) add(row_sum(r));
+    }
     const size_t o = base + (size_t)y * g.pitch + x;
     float ix, iy, it, nu, nv;
     unpack_coef(cpk[o], ix, iy, it);
-    hs_update(s.x, s.y, kf, ix, iy, it, inv[o], nu, nv);
+    if (w == 3) {
+        // canonical rule for w = 3: the column window y-1 .. y+1 is one aligned pair of rows and one single row;
+        // mean = fma(single, kf, kf * pair) (the fused kernel shares kf * pair between two rows: one packed
+        // multiply per two pixels instead of one per pixel)
+        const bool odd = ((y - 1 + g.grow0) & 1) != 0;                       // the window starts on an odd image row
+        const float2 single = odd ? row_sum(y - 1) : row_sum(y + 1);
+        const float2 pair = odd ? add2s(row_sum(y), row_sum(y + 1)) : add2s(row_sum(y - 1), row_sum(y));
+        const float ub = __fmaf_rn(single.x, kf, __fmul_rn(pair.x, kf));
+        const float vb = __fmaf_rn(single.y, kf, __fmul_rn(pair.y, kf));
+        hs_update_bar(ub, vb, ix, iy, it, inv[o], nu, nv);
+    } else {
+        hs_update(s.x, s.y, kf, ix, iy, it, inv[o], nu, nv);
+    }
     uvn[o] = make_float2(nu, nv);
 }
 
@@ -596,6 +612,11 @@ __device__ __forceinline__ void tile_sweeps(float2 (&uv)[R][4], const float2 (&g
             q[0][c] = add2(h[0][c], h[1][c]);
             q[1][c] = add2(h[2][c], h[3][c]);
         }
+        float2 qk[2][4];                               // w = 3 only: the pair sums times 1/9 (dead code otherwise)
+        if constexpr (RL == 1 && RR == 1 && !TB) {
+#pragma unroll
+            for (int c = 0; c < 4; ++c) { qk[0][c] = __fmul2_rn(q[0][c], kf2); qk[1][c] = __fmul2_rn(q[1][c], kf2); }
+        }
         // one patch row: paired box sum down the column from the row sums of rows j-RL..j+RR (the
         // patch's first row is an even image row), then the update
         auto column_term = [&](const float2 (&ab)[RL > 0 ? RL : 1][4], const float2 (&be)[RR > 0 ? RR : 1][4], int i, int c) {
@@ -631,7 +652,14 @@ __device__ __forceinline__ void tile_sweeps(float2 (&uv)[R][4], const float2 (&g
                         const float2 tt = column_term(ab, be, i, c);
                         sum = first ? tt : add2(sum, tt);
                     }
-                    bar = __fmul2_rn(sum, kf2);
+                    if constexpr (RL == 1 && RR == 1) {
+                        // w = 3 (canonical rule, see the header comment): the column window is one pair and one single
+                        // row; mean = fma(single, kf, kf * pair), the scaled pair sums being shared by two rows
+                        const float2 single = (j == 0) ? ab[0][c] : (j == 1 ? h[2][c] : (j == 2 ? h[1][c] : be[0][c]));
+                        bar = __ffma2_rn(single, kf2, qk[j >> 1][c]);
+                    } else {
+                        bar = __fmul2_rn(sum, kf2);
+                    }
                 }
                 float2 n = hs_update_bar2(bar, gxy[j][c], it[j][c], iv[j][c]);
                 if (MASKED) {
