@@ -18,8 +18,13 @@
 //   ubar = S_u * fl(1/w^2);  vbar likewise - except for w = 3, where the column window is always ONE pair of rows and
 //   ONE single row: ubar = fma(single, kf, kf * pair) with kf = fl(1/9), so that the fused kernel multiplies each
 //   shared pair sum once for the two rows that use it (6 % less FP32-pipe work per sweep, +3 % throughput)
-//   t = fma(Ix, ubar, fma(Iy, vbar, It));  c = t * inv;  u' = fma(-Ix, c, ubar);  v' = fma(-Iy, c, vbar)
-// with inv = 1 / (fl(alpha^2) + (Ix^2 + Iy^2)) rounded once (IEEE division) in K1.
+//   The update  u' = ubar - Ix (Ix ubar + Iy vbar + It) / den,  den = alpha^2 + Ix^2 + Iy^2  (hornSchunck.cpp:63-73) is
+//   evaluated with NORMALISED coefficients  P = Ix * s, Q = Iy * s, R = It * s,  s = 1 / sqrt(den):
+//       t = fma(P, ubar, fma(Q, vbar, R));  u' = fma(-P, t, ubar);  v' = fma(-Q, t, vbar)
+//   - algebraically the same (P t = Ix (..) / den), one multiply and one register per pixel less than the
+//   (Ix, Iy, It, 1/den) form, same accuracy against the fp64 oracle (4.1e-5 px on the hardest case either way).
+//   s = fl(1 / sqrt(fl(alpha^2) + (Ix^2 + Iy^2))) is rounded once (IEEE rsqrt) in K1 and stored in the `inv` plane;
+//   P, Q, R are single IEEE multiplies wherever a kernel unpacks a pixel.
 // Explicit __f*_rn intrinsics keep the compiler from re-associating or contracting differently
 // in different kernels.
 #pragma once
@@ -71,7 +76,7 @@ __device__ __forceinline__ int reflect101(int i, int n) {
 
 // ------------------------------------------------------------------------------------------
 // K1: spatio-temporal gradients + per-pixel coefficients, one pass over the two uint8 frames.
-// Writes {Ix,Iy,It} packed into one word per pixel (pack_coef) and inv = 1/(alpha^2+Ix^2+Iy^2)
+// Writes {Ix,Iy,It} packed into one word per pixel (pack_coef) and s = 1/sqrt(alpha^2+Ix^2+Iy^2)
 // as float: 8 B of coefficients per pixel.  4 pixels per thread, vector stores.
 // Frames: `frows` rows of `fpitch` bytes; buffer row y lives in frame row y + frow0 (frow0 = 1
 // when a seam row sits above).  BORDER_REFLECT_101 therefore only ever triggers at true image
@@ -115,7 +120,7 @@ k_grad_coeff(const uint8_t* __restrict__ prev, const uint8_t* __restrict__ next,
             gy = (d[i] + 2 * d[i + 1] + d[i + 2]) - (a[i] + 2 * a[i + 1] + a[i + 2]);      // :28
             gt = (int)n1[x] - c[i + 1];                                                    // :39
             const float den = __fadd_rn(alpha2, (float)(gx * gx + gy * gy));               // :65-68
-            iv = __fdiv_rn(1.0f, den);
+            iv = __frsqrt_rn(den);                                                         // s = 1/sqrt(den)
         }
         opk[i] = pack_coef(gx, gy, gt);
         oinv[i] = iv;
@@ -158,16 +163,16 @@ k_bgr2gray(const uint8_t* __restrict__ bgr, size_t bgr_pitch, uint8_t* __restric
 // ------------------------------------------------------------------------------------------
 // the per-pixel update, shared by K2 and K3 (hornSchunck.cpp:63-73)
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ void hs_update_bar(float ub, float vb, float ix, float iy, float it, float inv,
+__device__ __forceinline__ void hs_update_bar(float ub, float vb, float ix, float iy, float it, float s,
                                               float& un, float& vn) {
-    const float t = __fmaf_rn(ix, ub, __fmaf_rn(iy, vb, it));
-    const float c = __fmul_rn(t, inv);
-    un = __fmaf_rn(-ix, c, ub);
-    vn = __fmaf_rn(-iy, c, vb);
+    const float P = __fmul_rn(ix, s), Q = __fmul_rn(iy, s), R = __fmul_rn(it, s);
+    const float t = __fmaf_rn(P, ub, __fmaf_rn(Q, vb, R));
+    un = __fmaf_rn(-P, t, ub);
+    vn = __fmaf_rn(-Q, t, vb);
 }
 __device__ __forceinline__ void hs_update(float su, float sv, float kf, float ix, float iy,
-                                          float it, float inv, float& un, float& vn) {
-    hs_update_bar(__fmul_rn(su, kf), __fmul_rn(sv, kf), ix, iy, it, inv, un, vn);
+                                          float it, float s, float& un, float& vn) {
+    hs_update_bar(__fmul_rn(su, kf), __fmul_rn(sv, kf), ix, iy, it, s, un, vn);
 }
 
 // ---- "textbook" Horn-Schunck mode (HS_FLAG_TEXTBOOK; SURVEY 8f row 4, NOT a parity item: the
@@ -187,8 +192,8 @@ __device__ __forceinline__ void unpack_coef_tb(uint32_t w, float& ix, float& iy)
     ix = __fmul_rn(i4, 0.25f);
     iy = __fmul_rn(j4, 0.25f);
 }
-__device__ __forceinline__ float hs_inv(float ix, float iy, float alpha2) {
-    return __fdiv_rn(1.0f, __fadd_rn(alpha2, __fmaf_rn(ix, ix, __fmul_rn(iy, iy))));
+__device__ __forceinline__ float hs_inv(float ix, float iy, float alpha2) {      // s = 1 / sqrt(den)
+    return __frsqrt_rn(__fadd_rn(alpha2, __fmaf_rn(ix, ix, __fmul_rn(iy, iy))));
 }
 __device__ __forceinline__ float tb_bar(float V, float centre) {
     return __fmaf_rn(V, HS_TB_W12, __fmul_rn(centre, HS_TB_W3));
@@ -502,12 +507,12 @@ __device__ __forceinline__ float2 shfl_up2(float2 a) {
 __device__ __forceinline__ float2 shfl_down2(float2 a) {
     return make_float2(__shfl_down_sync(0xffffffffu, a.x, 1), __shfl_down_sync(0xffffffffu, a.y, 1));
 }
-// the per-pixel update on a packed average (hornSchunck.cpp:63-73), same operations as hs_update_bar:
-//   t = fma(Ix, ubar, fma(Iy, vbar, It));  c = t * inv;  {u', v'} = fma(-{Ix, Iy}, {c, c}, {ubar, vbar})
-__device__ __forceinline__ float2 hs_update_bar2(float2 bar, float2 ixy, float it, float inv) {
-    const float t = __fmaf_rn(ixy.x, bar.x, __fmaf_rn(ixy.y, bar.y, it));
-    const float c = __fmul_rn(t, inv);
-    return __ffma2_rn(make_float2(-ixy.x, -ixy.y), make_float2(c, c), bar);   // FFMA2 -R.F32x2, R.F32, R.F32x2
+// the per-pixel update on a packed average (hornSchunck.cpp:63-73), same operations as hs_update_bar with the
+// normalised coefficients pq = {P, Q}, r = R already formed:
+//   t = fma(P, ubar, fma(Q, vbar, R));  {u', v'} = fma(-{P, Q}, {t, t}, {ubar, vbar})
+__device__ __forceinline__ float2 hs_update_bar2(float2 bar, float2 pq, float r) {
+    const float t = __fmaf_rn(pq.x, bar.x, __fmaf_rn(pq.y, bar.y, r));
+    return __ffma2_rn(make_float2(-pq.x, -pq.y), make_float2(t, t), bar);   // FFMA2 -R.F32x2, R.F32, R.F32x2
 }
 
 // Paired window sums of 4 consecutive positions 0..3 (position 0 is even in absolute terms).
@@ -577,10 +582,10 @@ __device__ __forceinline__ void st_global_256(float2* dst, const float2 (&a)[4])
                  : "memory");
 }
 
-// k sweeps on a thread's 4 x R patch.  uv = {u, v} per pixel, gxy = {Ix, Iy}.
+// k sweeps on a thread's 4 x R patch.  uv = {u, v} per pixel, gxy = {P, Q}, it = R (normalised coefficients).
 template <int RL, int RR, int R, int NWARP, bool MASKED, bool TB>
 __device__ __forceinline__ void tile_sweeps(float2 (&uv)[R][4], const float2 (&gxy)[R][4],
-                                            const float (&it)[R][4], const float (&iv)[R][4],
+                                            const float (&it)[R][4],
                                             float* ex, int k, float kf, int warp, int lane,
                                             uint32_t inmask) {
     using TS = TileShape<RL, RR, R, NWARP>;
@@ -661,7 +666,7 @@ __device__ __forceinline__ void tile_sweeps(float2 (&uv)[R][4], const float2 (&g
                         bar = __fmul2_rn(sum, kf2);
                     }
                 }
-                float2 n = hs_update_bar2(bar, gxy[j][c], it[j][c], iv[j][c]);
+                float2 n = hs_update_bar2(bar, gxy[j][c], it[j][c]);
                 if (MASKED) {
                     const bool in = (inmask >> (j * 4 + c)) & 1u;
                     n.x = in ? n.x : 0.f;
@@ -1147,8 +1152,8 @@ k_jacobi_tile(const __grid_constant__ LaunchDesc<MAXS> d) {
         }
 
         const int swz = ((smem_u32(s_uv) >> 7) ^ (lane >> 2)) & 1;   // address bit 7 of the lane's chunk (rows are 1 KB)
-        float2 uv[R][4], gxy[R][4];        // {u, v} and {Ix, Iy} per pixel: packed-fp32 operands
-        float it[R][4], iv[R][4];
+        float2 uv[R][4], gxy[R][4];        // {u, v} and the normalised gradients {P, Q} per pixel: packed-fp32 operands
+        float it[R][4];                    // R = It * s
 #pragma unroll
         for (int j = 0; j < R; ++j) {
             const int so = (row0 + j) * TS::SX + lane * 4;
@@ -1159,20 +1164,21 @@ k_jacobi_tile(const __grid_constant__ LaunchDesc<MAXS> d) {
             const uint4 qc = *reinterpret_cast<const uint4*>(s_cpk + so);
             uv[j][0] = make_float2(q0.x, q0.y); uv[j][1] = make_float2(q0.z, q0.w);
             uv[j][2] = make_float2(q1.x, q1.y); uv[j][3] = make_float2(q1.z, q1.w);
-            if (TB) {       // second plane = It; inv from the gradients
-                it[j][0] = qi.x; it[j][1] = qi.y; it[j][2] = qi.z; it[j][3] = qi.w;
-                unpack_coef_tb(qc.x, gxy[j][0].x, gxy[j][0].y);
-                unpack_coef_tb(qc.y, gxy[j][1].x, gxy[j][1].y);
-                unpack_coef_tb(qc.z, gxy[j][2].x, gxy[j][2].y);
-                unpack_coef_tb(qc.w, gxy[j][3].x, gxy[j][3].y);
+            const float sc[4] = {qi.x, qi.y, qi.z, qi.w};     // second plane: s = 1 / sqrt(den) (textbook mode: It)
+            const uint32_t wc[4] = {qc.x, qc.y, qc.z, qc.w};
 #pragma unroll
-                for (int c = 0; c < 4; ++c) iv[j][c] = hs_inv(gxy[j][c].x, gxy[j][c].y, d.alpha2);
-            } else {
-                iv[j][0] = qi.x; iv[j][1] = qi.y; iv[j][2] = qi.z; iv[j][3] = qi.w;
-                unpack_coef(qc.x, gxy[j][0].x, gxy[j][0].y, it[j][0]);
-                unpack_coef(qc.y, gxy[j][1].x, gxy[j][1].y, it[j][1]);
-                unpack_coef(qc.z, gxy[j][2].x, gxy[j][2].y, it[j][2]);
-                unpack_coef(qc.w, gxy[j][3].x, gxy[j][3].y, it[j][3]);
+            for (int c = 0; c < 4; ++c) {      // (Ix, Iy, It) -> (P, Q, R): the same three multiplies as hs_update_bar
+                float ix, iy, itv, sv;
+                if (TB) {                      // s from the gradients
+                    unpack_coef_tb(wc[c], ix, iy);
+                    itv = sc[c];
+                    sv = hs_inv(ix, iy, d.alpha2);
+                } else {
+                    unpack_coef(wc[c], ix, iy, itv);
+                    sv = sc[c];
+                }
+                gxy[j][c] = __fmul2_rn(make_float2(ix, iy), make_float2(sv, sv));
+                it[j][c] = __fmul_rn(itv, sv);
             }
         }
         // Everyone has (a) finished the previous tile - its exchange scratch in the OTHER stage is
@@ -1188,9 +1194,9 @@ k_jacobi_tile(const __grid_constant__ LaunchDesc<MAXS> d) {
         float* s_ex = reinterpret_cast<float*>(st);
         const int kk = min(d.k, d.sweeps - cur_p * d.k);
         if (tile_inside)
-            tile_sweeps<RL, RR, R, NWARP, false, TB>(uv, gxy, it, iv, s_ex, kk, d.kf, warp, lane, inmask);
+            tile_sweeps<RL, RR, R, NWARP, false, TB>(uv, gxy, it, s_ex, kk, d.kf, warp, lane, inmask);
         else
-            tile_sweeps<RL, RR, R, NWARP, true, TB>(uv, gxy, it, iv, s_ex, kk, d.kf, warp, lane, inmask);
+            tile_sweeps<RL, RR, R, NWARP, true, TB>(uv, gxy, it, s_ex, kk, d.kf, warp, lane, inmask);
 
         HS_PROF_T(pt3);
         // store the exact centre of the tile into the other pair of planes
