@@ -217,7 +217,7 @@ int env_int(const char* name, int dflt) {
 //   tile load lost its bank conflicts, w=3 wanted k=4 while the working set sat in L2; now a staged tile is
 //   cheap enough to load that the deeper k wins everywhere.)
 //   Small and medium frames (less than three tiles per SM) choose k from a cost model of a phase
-//   (microseconds, fitted on B200 to profiles/r02w_k_sweep.jsonl and checked against it by
+//   (microseconds, fitted on B200 to profiles/r02al_k_sweep.jsonl and checked against it by
 //   tests/test_abi_cpu.py::test_default_k_is_near_the_measured_best):
 //     a tile costs          item(k)  = k * t_sweep + t_tile
 //     chained launches      phase(k) = ceil(tiles / #SMs) * item + t_launch     (tiles < 1.25 #SMs)
@@ -248,7 +248,7 @@ int choose_temporal_k(int asked, int W, int rows, int row_parity, int B, int RL,
     // keep a useful centre: at least a quarter of the staged rows must be output rows
     while (k > 1 && SY - (RL + RR) * k < SY / 4) --k;
     if (asked <= 0 && !seam && tiles(k) < (size_t)3 * num_sms) {
-        const double t_sweep = rad <= 1 ? 0.45 : 0.8, t_tile = 1.2, t_launch = 3.0, t_dep = 6.0, t_coop = 40.0;
+        const double t_sweep = rad <= 1 ? 0.38 : 0.7, t_tile = 1.2, t_launch = 4.0, t_dep = 6.0, t_coop = 40.0;
         int kcap = std::min(kmax, rad <= 1 ? 12 : 7);
         if (max_iterations > 0) kcap = std::min(kcap, max_iterations);
         const int T = max_iterations > 0 ? max_iterations : 1000;

@@ -32,6 +32,7 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <type_traits>
 
 namespace hs {
 
@@ -594,9 +595,12 @@ __device__ __forceinline__ void tile_sweeps(float2 (&uv)[R][4], const float2 (&g
     const int wa = warp > 0 ? warp - 1 : 0;
     const int wb = warp < NWARP - 1 ? warp + 1 : NWARP - 1;
     const float2 kf2 = make_float2(kf, kf);
-    for (int s = 0; s < k; ++s) {
+    // one sweep; PAR = parity of the sweep = which of the two exchange arrays it uses.  The loop below is unrolled
+    // by two so that PAR is a compile-time constant and every exchange address is base + immediate (the address
+    // arithmetic per sweep was ~10 integer instructions, half of them IMADs on the FP32 pipe)
+    auto sweep = [&](auto PAR) {
         // exchange array of this sweep parity: [NWARP][NSLOT][SX] float2 = {row sum of u, row sum of v}
-        float2* exs = reinterpret_cast<float2*>(ex) + (size_t)(s & 1) * TS::EX_FIELD;
+        float2* exs = reinterpret_cast<float2*>(ex) + (size_t)decltype(PAR)::value * TS::EX_FIELD;
         float2 h[R][4];
 #pragma unroll
         for (int j = 0; j < R; ++j) {
@@ -699,7 +703,13 @@ __device__ __forceinline__ void tile_sweeps(float2 (&uv)[R][4], const float2 (&g
 #pragma unroll
         for (int j = 0; j < R; ++j)
             if (j < RL || j >= R - RR) update_row(j, ab, be);
+    };
+    int s = 0;
+    for (; s + 2 <= k; s += 2) {
+        sweep(std::integral_constant<int, 0>{});
+        sweep(std::integral_constant<int, 1>{});
     }
+    if (s < k) sweep(std::integral_constant<int, 0>{});
 }
 
 #ifdef HS_TILE_PROFILE

@@ -159,12 +159,12 @@ def test_slab_plan_is_pure_host_arithmetic(pkg):
 def test_default_k_is_near_the_measured_best(pkg):
     """The temporal-blocking depth hs_create picks (hs_default_temporal_k: defaults measured for large frames, a
     phase cost model for small ones) against the k sweep measured on B200 with this kernel
-    (profiles/r02w_k_sweep.jsonl, tools/gpu_sweep.py): within 5 % of the best k for every size and window."""
+    (profiles/r02al_k_sweep.jsonl, tools/gpu_sweep.py): within 5 % of the best k for every size and window."""
     import collections
     import json
     from cpp_optical_flow_b200 import hs_ctypes as H
     lib = pkg.load_library()
-    rows = [json.loads(l) for l in open(os.path.join(ROOT, "profiles", "r02w_k_sweep.jsonl")) if l.startswith("{")]
+    rows = [json.loads(l) for l in open(os.path.join(ROOT, "profiles", "r02al_k_sweep.jsonl")) if l.startswith("{")]
     by = collections.defaultdict(dict)
     for r in rows:
         if "error" not in r:
