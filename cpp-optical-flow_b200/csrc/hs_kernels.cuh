@@ -607,11 +607,12 @@ __device__ __forceinline__ void tile_sweeps(float2 (&uv)[R][4], const float2 (&g
             if (TB) row_sums_tb(uv[j], h[j]);
             else row_sums<RL, RR>(uv[j], h[j]);
             if (TS::slot(j) >= 0) {  // rows a vertical neighbour will need
-                // a row is stored as two halves of 32 lanes x 16 B (pixels 0-1 of every lane, then pixels
-                // 2-3): consecutive lanes hit consecutive 16-byte chunks, no bank conflicts
-                float4* o = reinterpret_cast<float4*>(exs + ((size_t)warp * TS::NSLOT + TS::slot(j)) * TS::SX) + lane;
-                o[0] = make_float4(h[j][0].x, h[j][0].y, h[j][1].x, h[j][1].y);
-                o[32] = make_float4(h[j][2].x, h[j][2].y, h[j][3].x, h[j][3].y);
+                // a row is stored as four quarters of 32 lanes x 8 B (pixel c of every lane): each {u, v} sum is a
+                // register pair already, so these are plain STS.64 / LDS.64 (two STS.128 per row needed seven
+                // MOVs to line their operands up; same number of shared-memory wavefronts either way)
+                float2* o = exs + ((size_t)warp * TS::NSLOT + TS::slot(j)) * TS::SX + lane;
+#pragma unroll
+                for (int c = 0; c < 4; ++c) o[32 * c] = h[j][c];
             }
         }
         static_assert(R == 4, "the shared column pairs below are (0,1) and (2,3)");
@@ -688,17 +689,15 @@ __device__ __forceinline__ void tile_sweeps(float2 (&uv)[R][4], const float2 (&g
         // neighbour rows: the last RL rows of the patch above, the first RR rows of the patch below
 #pragma unroll
         for (int i = 0; i < RL; ++i) {
-            const float4* o = reinterpret_cast<const float4*>(exs + ((size_t)wa * TS::NSLOT + TS::slot(R - RL + i)) * TS::SX) + lane;
-            const float4 a0 = o[0], a1 = o[32];
-            ab[i][0] = make_float2(a0.x, a0.y); ab[i][1] = make_float2(a0.z, a0.w);
-            ab[i][2] = make_float2(a1.x, a1.y); ab[i][3] = make_float2(a1.z, a1.w);
+            const float2* o = exs + ((size_t)wa * TS::NSLOT + TS::slot(R - RL + i)) * TS::SX + lane;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) ab[i][c] = o[32 * c];
         }
 #pragma unroll
         for (int i = 0; i < RR; ++i) {
-            const float4* o = reinterpret_cast<const float4*>(exs + ((size_t)wb * TS::NSLOT + TS::slot(i)) * TS::SX) + lane;
-            const float4 a0 = o[0], a1 = o[32];
-            be[i][0] = make_float2(a0.x, a0.y); be[i][1] = make_float2(a0.z, a0.w);
-            be[i][2] = make_float2(a1.x, a1.y); be[i][3] = make_float2(a1.z, a1.w);
+            const float2* o = exs + ((size_t)wb * TS::NSLOT + TS::slot(i)) * TS::SX + lane;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) be[i][c] = o[32 * c];
         }
 #pragma unroll
         for (int j = 0; j < R; ++j)
