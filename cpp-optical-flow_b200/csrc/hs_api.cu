@@ -230,7 +230,7 @@ inline int large_frame_k(int RL, int RR) {
     return w <= 2 ? 8 : (w == 3 ? 6 : (w == 4 ? 4 : (w == 5 ? 3 : 2)));
 }
 int choose_temporal_k(int asked, int W, int rows, int row_parity, int B, int RL, int RR, int max_iterations, int num_sms,
-                      bool may_dataflow, bool seam, double plane_px) {
+                      bool may_dataflow, bool seam) {
     const int SY = TILE_R * TILE_NWARP, SX = 128;
     const int kmax = (SY - 3) / std::max(1, RL + RR);
     const int rad = std::max(RL, RR);
@@ -243,7 +243,6 @@ int choose_temporal_k(int asked, int W, int rows, int row_parity, int B, int RL,
     };
     int k = asked;
     if (k <= 0) k = large_frame_k(RL, RR);
-    (void)plane_px;
     k = std::min(k, kmax);
     // keep a useful centre: at least a quarter of the staged rows must be output rows
     while (k > 1 && SY - (RL + RR) * k < SY / 4) --k;
@@ -761,7 +760,7 @@ int hs_default_temporal_k(const hs_config* cfg_in, int32_t num_sms) {
     int r0 = cfg.out_row_begin, r1 = cfg.out_row_end;
     if (r0 == 0 && r1 == 0) r1 = cfg.height;
     return choose_temporal_k(cfg.temporal_k, cfg.width, r1 - r0, r0 + cfg.global_row0, B, RL, RR, cfg.max_iterations, num_sms,
-                             !(cfg.flags & HS_FLAG_SINGLE_PHASE), seam, (double)round_up(cfg.width, 32) * cfg.height * B);
+                             !(cfg.flags & HS_FLAG_SINGLE_PHASE), seam);
 }
 
 const char* hs_last_error(const hs_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_err.c_str(); }
@@ -920,7 +919,7 @@ int create_single(const hs_config& cfg_in, hs_ctx** out) {
         const bool may_dataflow = !(cfg.flags & HS_FLAG_SINGLE_PHASE) && env_int("HS_SINGLE_PHASE", 0) == 0;
         const int k = choose_temporal_k(cfg.temporal_k > 0 ? cfg.temporal_k : env_int("HS_K", 0), c->W, c->oy1 - c->oy0,
                                         c->oy0 + c->grow0, c->B, c->RL, c->RR, cfg.max_iterations, c->num_sms,
-                                        may_dataflow, c->top_seam || c->bot_seam, (double)c->plane * c->B);
+                                        may_dataflow, c->top_seam || c->bot_seam);
         (void)kmax;
         c->k = k;
         c->kernel_id = 1;

@@ -622,7 +622,7 @@ __device__ __forceinline__ void tile_sweeps(float2 (&uv)[R][4], const float2 (&g
             q[0][c] = add2(h[0][c], h[1][c]);
             q[1][c] = add2(h[2][c], h[3][c]);
         }
-        float2 qk[2][4];                               // w = 3 only: the pair sums times 1/9 (dead code otherwise)
+        [[maybe_unused]] float2 qk[2][4];              // w = 3 only: the pair sums times 1/9 (dead code otherwise)
         if constexpr (RL == 1 && RR == 1 && !TB) {
 #pragma unroll
             for (int c = 0; c < 4; ++c) { qk[0][c] = __fmul2_rn(q[0][c], kf2); qk[1][c] = __fmul2_rn(q[1][c], kf2); }

@@ -47,11 +47,9 @@ bool plan_slab(int H, int world, int rank, int RL, int RR, int k, SlabPlan* p, s
 
 // default temporal-blocking depth of a slab (same rule as create_single for large frames; the slabs of
 // one image must all use the same k, so it is chosen once here)
-int pick_slab_k(const hs_config& cfg, int RL, int RR, int rows) {
+int pick_slab_k(const hs_config& cfg, int RL, int RR) {
     int k = cfg.temporal_k > 0 ? cfg.temporal_k : env_int("HS_K", 0);
-    const int rad = std::max(RL, RR);
     if (k <= 0) k = large_frame_k(RL, RR);
-    (void)rows; (void)rad;
     const int SY = TILE_R * TILE_NWARP;
     k = std::min(k, (SY - 3) / std::max(1, RL + RR));
     while (k > 1 && SY - (RL + RR) * k < SY / 4) --k;
@@ -180,7 +178,7 @@ int create_slab_rank(const hs_config& cfg, hs_ctx** out) {
     const int a = cfg.window_size - cfg.window_size / 2 - 1, RL = a, RR = cfg.window_size - 1 - a;
     SlabPlan p0;
     std::string why;
-    const int k = pick_slab_k(cfg, RL, RR, (cfg.height + cfg.slab_world - 1) / cfg.slab_world);
+    const int k = pick_slab_k(cfg, RL, RR);
     if (!plan_slab(cfg.height, cfg.slab_world, cfg.slab_rank, RL, RR, k, &p0, &why)) return fail(nullptr, HS_ERR_INVALID_ARG, "%s", why.c_str());
     hs_config cc = child_config(cfg, p0, k, cfg.device, cfg.stream);
     int rc = create_single(cc, out);
@@ -335,7 +333,7 @@ int create_group(const hs_config& cfg, hs_ctx** out) {
         g->emulate = all_same;
         if (g->emulate && n > EMU_MAXS) return bail(fail(g, HS_ERR_UNSUPPORTED, "at most %d row slabs on one device", EMU_MAXS));
         if (g->emulate && g->exchange == HS_EXCHANGE_NCCL) return bail(fail(g, HS_ERR_UNSUPPORTED, "HS_EXCHANGE_NCCL needs distinct devices"));
-        const int k = pick_slab_k(cfg, g->RL, g->RR, (cfg.height + n - 1) / n);
+        const int k = pick_slab_k(cfg, g->RL, g->RR);
         void* shared_stream = nullptr;
         for (int i = 0; i < n; ++i) {
             SlabPlan p;
