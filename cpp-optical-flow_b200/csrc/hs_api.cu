@@ -980,6 +980,11 @@ void hs_destroy(hs_ctx* ctx) { destroy_impl(ctx); }
 #define HS_NO_F64(c, name)                                                                                \
     if ((c)->f64) return fail((c), HS_ERR_UNSUPPORTED, name " is not available on an HS_PREC_F64 context")
 
+// an hs_solve_async call is in flight: its buffers and planes must not be touched until hs_solve_wait
+#define HS_NO_ASYNC(c, name)                                                                              \
+    if ((c)->async_pending)                                                                               \
+        return fail((c), HS_ERR_STATE, name ": an hs_solve_async call is in flight on this context (hs_solve_wait first)")
+
 #define HS_NO_GROUP(c, name)                                                                              \
     if (!(c)->kids.empty())                                                                               \
         return fail((c), HS_ERR_UNSUPPORTED, name " is not available on a multi-device context (use hs_solve, "   \
@@ -987,6 +992,7 @@ void hs_destroy(hs_ctx* ctx) { destroy_impl(ctx); }
 
 int hs_upload(hs_ctx* c, const uint8_t* prev, size_t ps, size_t pis, const uint8_t* next, size_t ns, size_t nis) {
     if (!c) return HS_ERR_INVALID_ARG;
+    HS_NO_ASYNC(c, "hs_upload");
     if (!c->kids.empty()) return group_upload(c, prev, ps, pis, next, ns, nis);
     DevGuard g(c->dev);
     return do_upload(c, prev, ps, pis, next, ns, nis);
@@ -994,6 +1000,7 @@ int hs_upload(hs_ctx* c, const uint8_t* prev, size_t ps, size_t pis, const uint8
 
 int hs_prepare(hs_ctx* c) {
     if (!c) return HS_ERR_INVALID_ARG;
+    HS_NO_ASYNC(c, "hs_prepare");
     if (!c->kids.empty()) return group_prepare(c);
     DevGuard g(c->dev);
     return do_prepare(c);
@@ -1001,6 +1008,7 @@ int hs_prepare(hs_ctx* c) {
 
 int hs_iterate(hs_ctx* c, int iterations) {
     if (!c) return HS_ERR_INVALID_ARG;
+    HS_NO_ASYNC(c, "hs_iterate");
     if (!c->kids.empty()) {
         if (!c->prepared) return fail(c, HS_ERR_STATE, "hs_iterate before hs_prepare");
         return group_iterate(c, iterations);
@@ -1066,6 +1074,7 @@ int hs_iterate_until(hs_ctx* c, int max_sweeps, double tolerance, int check_ever
 
 int hs_solve_device(hs_ctx* c) {
     if (!c) return HS_ERR_INVALID_ARG;
+    HS_NO_ASYNC(c, "hs_solve_device");
     if (!c->kids.empty()) return group_solve_device(c);
     if (c->top_seam || c->bot_seam)
         return fail(c, HS_ERR_UNSUPPORTED, "hs_solve_device on a row-slab context: halos must be refreshed every "
@@ -1084,6 +1093,7 @@ int hs_solve_device(hs_ctx* c) {
 
 int hs_download(hs_ctx* c, void* u, size_t us, size_t uis, void* v, size_t vs, size_t vis, int dt) {
     if (!c) return HS_ERR_INVALID_ARG;
+    HS_NO_ASYNC(c, "hs_download");
     if (!c->kids.empty()) {
         int rc = group_download(c, u, us, uis, v, vs, vis, dt);
         return rc ? rc : group_sync(c);
@@ -1113,6 +1123,7 @@ int hs_sync(hs_ctx* c) {
 int hs_solve(hs_ctx* c, const uint8_t* prev, size_t ps, size_t pis, const uint8_t* next, size_t ns, size_t nis,
              void* u, size_t us, size_t uis, void* v, size_t vs, size_t vis, int dt) {
     if (!c) return HS_ERR_INVALID_ARG;
+    HS_NO_ASYNC(c, "hs_solve");
     if (!c->kids.empty()) return group_solve(c, prev, ps, pis, next, ns, nis, u, us, uis, v, vs, vis, dt);
     if (c->top_seam || c->bot_seam)
         return fail(c, HS_ERR_UNSUPPORTED, "hs_solve on a row-slab context: halos must be refreshed every temporal_k "
@@ -1190,6 +1201,7 @@ int hs_solve_wait(hs_ctx* c) {
 int hs_solve_bgr(hs_ctx* c, const uint8_t* prev, size_t ps, const uint8_t* next, size_t ns,
                  void* u, size_t us, void* v, size_t vs, int dt) {
     if (!c) return HS_ERR_INVALID_ARG;
+    HS_NO_ASYNC(c, "hs_solve_bgr");
     HS_NO_GROUP(c, "hs_solve_bgr");
     HS_NO_F64(c, "hs_solve_bgr");
     if (c->B != 1 || c->top_seam || c->bot_seam)
@@ -1233,6 +1245,7 @@ int hs_solve_bgr(hs_ctx* c, const uint8_t* prev, size_t ps, const uint8_t* next,
 int hs_gradients(hs_ctx* c, const uint8_t* prev, size_t ps, const uint8_t* next, size_t ns, void* gx, void* gy,
                  void* gt, size_t os, int dt) {
     if (!c) return HS_ERR_INVALID_ARG;
+    HS_NO_ASYNC(c, "hs_gradients");
     HS_NO_GROUP(c, "hs_gradients");
     if (c->B != 1) return fail(c, HS_ERR_UNSUPPORTED, "hs_gradients needs a batch == 1 context");
     if (!gx || !gy || !gt) return fail(c, HS_ERR_INVALID_ARG, "null output pointer");
@@ -1402,6 +1415,7 @@ extern "C" int hs_video_push(hs_ctx* c, const uint8_t* frame, size_t stride, voi
                              int dt, int* pair_index) {
     if (!c || !pair_index) return HS_ERR_INVALID_ARG;
     *pair_index = -1;
+    HS_NO_ASYNC(c, "hs_video_push");
     HS_NO_GROUP(c, "hs_video_push");
     HS_NO_F64(c, "hs_video_push");
     if (!frame) return fail(c, HS_ERR_INVALID_ARG, "null frame pointer");

@@ -389,6 +389,8 @@ def test_async_solves_on_a_shared_stream_equal_synchronous_solves(pkg):
     enqueue(0)
     with pytest.raises(H.HsError):
         ctxs[0].solve_async_raw(hp[0].data_ptr(), hn[0].data_ptr(), Ww, 0, outs[0][0].data_ptr(), outs[0][1].data_ptr(), Ww * 8, 0, H.HS_F64)
+    with pytest.raises(H.HsError):                            # ... and so is any other use of its buffers
+        ctxs[0].solve(pairs[0][0], pairs[0][1], np.float32)
     for i in range(len(pairs)):
         if i + 1 < len(pairs):
             enqueue(i + 1)
